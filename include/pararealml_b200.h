@@ -1,0 +1,122 @@
+/*
+ * C ABI of the B200-native FDM + Parareal hot path (libpararealml_b200.so).
+ *
+ * The reference (ViktorC/PararealML v0.3.0) is pure Python and has no FFI; the
+ * entry points below are what a binding for its hot path would call, each
+ * citing the reference code it replaces.  All pointers named *_dev are device
+ * pointers owned by the caller (PyTorch tensors in the shipped host layer);
+ * nothing is allocated per call.  Functions return 0 on success and a negative
+ * code on failure, pml_last_error() then holds a message.  A plan is
+ * thread-compatible, not thread-safe.
+ */
+#ifndef PARAREALML_B200_H
+#define PARAREALML_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pml_plan pml_plan;
+
+enum { PML_INTEGRATOR_FORWARD_EULER = 0, PML_INTEGRATOR_EXPLICIT_MIDPOINT = 1,
+       PML_INTEGRATOR_RK4 = 2 };
+
+typedef struct pml_plan_desc {
+  int n_dims;       /* 0 (ODE) .. 3 */
+  int shape[3];     /* mesh vertices per axis, trailing unused axes = 1 */
+  int y_dim;        /* components of y */
+  int n_dt, n_alg, n_lap; /* equations per LHS kind (differential_equation.py:140-149) */
+  int block[3];     /* thread block shape the source was generated for */
+} pml_plan_desc;
+
+/* NaN-coded boundary tables and 1-D coordinate vectors (device pointers).
+ * Face index = axis * 2 + side.  Replaces the Constraint objects of
+ * constrained_problem.py:303-476 / constraint.py:6-101 on the device. */
+typedef struct pml_tables {
+  const double* neu[6];
+  long long neu_stride[6]; /* doubles between time slots, 0 = static */
+  const double* dir[6];
+  long long dir_stride[6];
+  const double* coord[3];  /* mesh.vertex_axis_coordinates (mesh.py:353) */
+  const double* aux[4];    /* 1/r[i0], sin(phi)[i2], cos(phi)[i2], 1/sin(phi)[i2] */
+} pml_tables;
+
+/* Scratch buffers, each y_dim * n_cells doubles unless noted. */
+typedef struct pml_workspace {
+  double* u_a;
+  double* u_b;
+  double* acc;
+  double* lap_rhs;   /* n_lap * n_cells */
+  double* jac_a;     /* n_lap * n_cells */
+  double* jac_b;     /* n_lap * n_cells */
+  double* partials;  /* one double per thread block */
+  int* flags;        /* 2 ints: done, sweeps */
+} pml_workspace;
+
+const char* pml_last_error(void);
+int pml_version(void);
+
+/* Compiles (NVRTC, sm_100a) the generated stage-kernel source, or loads the
+ * cubin cached at cubin_path if that file exists (it is written otherwise;
+ * may be NULL).  Replaces FDMSymbolMapper construction + sp.lambdify
+ * (symbol_mapper.py:28-42, 222-253). */
+int pml_plan_create(const char* source, const pml_plan_desc* desc,
+                    const char* cubin_path, pml_plan** plan);
+/* NVRTC only, no GPU needed: compiles to a cubin file (build-time check). */
+int pml_compile_to_cubin(const char* source, const char* cubin_path);
+int pml_plan_destroy(pml_plan* plan);
+int pml_plan_set_tables(pml_plan* plan, const pml_tables* tables);
+long long pml_plan_launches(const pml_plan* plan); /* kernels launched so far */
+
+/* n_steps explicit time steps, asynchronous on `stream` unless n_lap > 0.
+ * Step j reads y0_dev (j == 0) or trajectory slot j-1 and writes slot j.
+ * t_host[j] is the step's start time (operator.py:60-74); boundary table slot
+ * of step j, stage time q in {t, t + dt/2, t + dt} is slot0 + 3 j + q.
+ * Replaces the time loop and y_next function of fdm_operator.py:48-165 and
+ * the integrators of numerical_integrator.py:47-132. */
+int pml_fdm_run(pml_plan* plan, int integrator, const pml_workspace* ws,
+                const double* y0_dev, double* traj_dev,
+                long long traj_step_stride, const double* t_host, int n_steps,
+                double d_t, long long slot0, const double* jacobi_init_dev,
+                double jacobi_tol, long long max_sweeps, int* sweeps_out_host,
+                void* stream);
+
+/* One evaluation of the generated right-hand sides (differentiator entry
+ * points, numerical_differentiator.py:114-870). */
+int pml_eval_rhs(pml_plan* plan, const double* u_dev, double* out_dev, double t,
+                 long long slot, void* stream);
+
+/* Jacobi anti-Laplacian on its own (numerical_differentiator.py:872-927). */
+int pml_jacobi_run(pml_plan* plan, const pml_workspace* ws,
+                   const double* rhs_dev, const double* y_init_dev,
+                   double* y_next_dev, long long slot, double tol,
+                   long long max_sweeps, int* sweeps_out_host, void* stream);
+
+/* Layout conversion between the reference's channels-last (*mesh, C) arrays
+ * and the device's component planes, batched over n_states. */
+int pml_aos_to_soa(const double* aos_dev, double* soa_dev, long long n_cells,
+                   int y_dim, long long n_states, void* stream);
+int pml_soa_to_aos(const double* soa_dev, double* aos_dev, long long n_cells,
+                   int y_dim, long long n_states, void* stream);
+
+/* Parareal device helpers (parareal_operator.py:164, 183-185, 85-100, 192).
+ * States are component planes of n_cells doubles. */
+int pml_parareal_correction(const double* fine_end_dev,
+                            const double* coarse_end_dev, double* corr_dev,
+                            long long n, void* stream);
+/* new_end = coarse_end + corr; sumsq_dev[c] = sum over cells of
+ * (new_end - old_end)^2 for component c (deterministic two-pass reduction;
+ * scratch_dev needs y_dim * 1024 doubles). */
+int pml_parareal_update(const double* coarse_end_dev, const double* corr_dev,
+                        const double* old_end_dev, double* new_end_dev,
+                        double* sumsq_dev, double* scratch_dev,
+                        long long n_cells, int y_dim, void* stream);
+/* traj[s] += new_end - traj[n_steps - 1] for every step s (rigid shift). */
+int pml_parareal_shift(double* traj_dev, long long n_steps,
+                       long long step_stride, const double* new_end_dev,
+                       double* delta_scratch_dev, long long n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,508 @@
+// ---------------------------------------------------------------------------
+// Fixed CUDA template of the fused FDM stage kernels (sm_100a, fp64).
+//
+// This file is appended to a GENERATED prelude (pararealml_b200/operators/fdm/
+// codegen.py) that #defines the mesh, the equation system and the pointwise
+// right-hand side emitted from the SymPy system with SymPy's C printer, and is
+// compiled at run time with NVRTC (-arch=sm_100a).  It replaces, for one
+// (problem, integrator) pair, the reference's
+//   * ThreePointCentralDifferenceMethod._derivative / _second_derivative /
+//     _add_halos_along_axis   (numerical_differentiator.py:1012-1095,1188-1242)
+//   * the coordinate-system algebra of gradient/hessian/divergence/curl/
+//     laplacian (numerical_differentiator.py:114-725; emitted by the generator
+//     in terms of the primitives below)
+//   * RK4 / ExplicitMidpoint / ForwardEuler stage arithmetic and the Dirichlet
+//     overwrite after every stage (numerical_integrator.py:47-132,
+//     constraint.py:43-58)
+//   * the LHS.Y overwrite and the LHS.Y_LAPLACIAN Jacobi solve
+//     (fdm_operator.py:127-161, numerical_differentiator.py:872-927,1097-1186)
+//
+// Data layout: SoA planes, plane c of a state at base + c * PML_NCELLS, cells
+// in C order of the mesh axes (last mesh axis contiguous).  Unused trailing
+// axes have extent 1.  Boundary tables are NaN-coded (NaN = unconstrained),
+// channels-last (face cell, component), one table per (axis, side).
+//
+// Prelude contract (all compile-time):
+//   PML_NDIM, PML_C, PML_N0, PML_N1, PML_N2, PML_COORD (0 cart, 1 polar,
+//   2 cylindrical, 3 spherical), PML_NEU_MASK / PML_DIR_MASK (bit axis*2+side),
+//   PML_H0..2, PML_INV2H0..2, PML_INVHH0..2 (spacing constants),
+//   PML_NDT / PML_NALG / PML_NLAP and the index lists PML_DT_IDX, PML_ALG_IDX,
+//   PML_LAP_IDX, PML_KIND[c] (0 dt, 1 algebraic, 2 laplacian),
+//   PML_PASSTHROUGH (non-dt components of stage inputs are read from y),
+//   PML_BX/BY/BZ thread block shape, PML_JAC_INV_DIAG,
+//   and the generated functions pml_rhs_dt(), pml_rhs_aux().
+// ---------------------------------------------------------------------------
+
+typedef long long i64;
+
+#define PML_NCELLS ((i64)PML_N0 * (i64)PML_N1 * (i64)PML_N2)
+#define PML_NAN __longlong_as_double(0x7ff8000000000000LL)
+
+struct PmlArgs {
+  const double* u;        // stencil input of this stage (C planes)
+  const double* y;        // state at the start of the step (C planes)
+  const double* acc_in;   // RK4 accumulator (C planes, dt components used)
+  double* u_out;          // next stage input
+  double* acc_out;
+  double* y_next;         // trajectory slot of this step
+  double* lap_rhs;        // right-hand sides of the Y_LAPLACIAN equations
+  double t_eval;          // time the right-hand side is evaluated at
+  double dt;
+  i64 neu_slot;           // boundary table slots (dynamic conditions)
+  i64 dir_slot;           // Dirichlet slot of this stage's output
+  i64 dir_slot_full;      // Dirichlet slot of t + dt (algebraic equations)
+  const double* neu[6];   // Neumann tables per face (axis * 2 + side)
+  i64 neu_stride[6];      // doubles per slot (0 = static)
+  const double* dir[6];   // Dirichlet tables per face
+  i64 dir_stride[6];
+  const double* coord[3];  // vertex coordinates along each axis
+  const double* aux[4];    // 1/r[i0], sin(phi)[i2], cos(phi)[i2], 1/sin(phi)[i2]
+};
+
+template <int A> struct PmlAx;
+template <> struct PmlAx<0> {
+  static constexpr int N = PML_N0;
+  static constexpr i64 S = (i64)PML_N1 * (i64)PML_N2;
+  static constexpr double H = PML_H0, INV2H = PML_INV2H0, INVHH = PML_INVHH0;
+};
+template <> struct PmlAx<1> {
+  static constexpr int N = PML_N1;
+  static constexpr i64 S = (i64)PML_N2;
+  static constexpr double H = PML_H1, INV2H = PML_INV2H1, INVHH = PML_INVHH1;
+};
+template <> struct PmlAx<2> {
+  static constexpr int N = PML_N2;
+  static constexpr i64 S = 1;
+  static constexpr double H = PML_H2, INV2H = PML_INV2H2, INVHH = PML_INVHH2;
+};
+
+struct PmlCell {
+  int i0, i1, i2;
+  i64 idx;
+};
+
+template <int A> __device__ __forceinline__ int pml_ia(int i0, int i1, int i2) {
+  return A == 0 ? i0 : (A == 1 ? i1 : i2);
+}
+
+__device__ __forceinline__ i64 pml_lin(int i0, int i1, int i2) {
+  return ((i64)i0 * PML_N1 + i1) * PML_N2 + i2;
+}
+
+// index of a cell within the boundary face normal to axis A
+template <int A> __device__ __forceinline__ i64 pml_face(int i0, int i1, int i2) {
+  return A == 0 ? (i64)i1 * PML_N2 + i2
+                : (A == 1 ? (i64)i0 * PML_N2 + i2 : (i64)i0 * PML_N1 + i1);
+}
+
+#if PML_COHERENT_LOADS
+// single-CTA time loop: data written earlier in the same launch is re-read
+#define PML_LD(p) (*(const volatile double*)(p))
+#else
+#define PML_LD(p) __ldg(p)
+#endif
+
+template <int A, int SIDE>
+__device__ __forceinline__ double pml_neu(const PmlArgs& a, int comp, int i0,
+                                          int i1, int i2) {
+  constexpr int f = A * 2 + SIDE;
+  if (!((PML_NEU_MASK >> f) & 1)) return PML_NAN;
+  return __ldg(a.neu[f] + a.neu_slot * a.neu_stride[f] +
+               pml_face<A>(i0, i1, i2) * PML_C + comp);
+}
+
+// first derivative along A at an arbitrary cell: zero ghost cells, boundary
+// planes overwritten by the Neumann value where one exists
+template <int A>
+__device__ __forceinline__ double pml_d1_at(const PmlArgs& a,
+                                            const double* __restrict__ p,
+                                            int comp, int i0, int i1, int i2) {
+  typedef PmlAx<A> X;
+  const int ia = pml_ia<A>(i0, i1, i2);
+  const i64 idx = pml_lin(i0, i1, i2);
+  const double lo = ia > 0 ? PML_LD(p + idx - X::S) : 0.0;
+  const double hi = ia < X::N - 1 ? PML_LD(p + idx + X::S) : 0.0;
+  double d = (hi - lo) * X::INV2H;
+  if (((PML_NEU_MASK >> (A * 2)) & 1) && ia == 0) {
+    const double g = pml_neu<A, 0>(a, comp, i0, i1, i2);
+    if (g == g) d = g;
+  }
+  if (((PML_NEU_MASK >> (A * 2 + 1)) & 1) && ia == X::N - 1) {
+    const double g = pml_neu<A, 1>(a, comp, i0, i1, i2);
+    if (g == g) d = g;
+  }
+  return d;
+}
+
+// neighbour sum / difference helpers with the second-difference ghost rule:
+// ghost = inner neighbour -/+ 2 h g where a Neumann value g exists, else 0
+template <int A>
+__device__ __forceinline__ void pml_nb2(const PmlArgs& a,
+                                        const double* __restrict__ p, int comp,
+                                        int i0, int i1, int i2, double& lo,
+                                        double& hi) {
+  typedef PmlAx<A> X;
+  const int ia = pml_ia<A>(i0, i1, i2);
+  const i64 idx = pml_lin(i0, i1, i2);
+  if (ia > 0) {
+    lo = PML_LD(p + idx - X::S);
+  } else {
+    lo = 0.0;
+    if ((PML_NEU_MASK >> (A * 2)) & 1) {
+      const double g = pml_neu<A, 0>(a, comp, i0, i1, i2);
+      if (g == g) lo = PML_LD(p + idx + X::S) + (-2.0 * X::H) * g;
+    }
+  }
+  if (ia < X::N - 1) {
+    hi = PML_LD(p + idx + X::S);
+  } else {
+    hi = 0.0;
+    if ((PML_NEU_MASK >> (A * 2 + 1)) & 1) {
+      const double g = pml_neu<A, 1>(a, comp, i0, i1, i2);
+      if (g == g) hi = PML_LD(p + idx - X::S) + (2.0 * X::H) * g;
+    }
+  }
+}
+
+template <int A>
+__device__ __forceinline__ double pml_d2_at(const PmlArgs& a,
+                                            const double* __restrict__ p,
+                                            int comp, int i0, int i1, int i2) {
+  double lo, hi;
+  pml_nb2<A>(a, p, comp, i0, i1, i2, lo, hi);
+  const double c = PML_LD(p + pml_lin(i0, i1, i2));
+  return ((hi - 2.0 * c) + lo) * PmlAx<A>::INVHH;
+}
+
+// mixed second derivative: constrained d/dA, then unconstrained zero-ghost d/dB
+template <int A, int B>
+__device__ __forceinline__ double pml_d2m_at(const PmlArgs& a,
+                                             const double* __restrict__ p,
+                                             int comp, int i0, int i1, int i2) {
+  typedef PmlAx<B> X;
+  const int ib = pml_ia<B>(i0, i1, i2);
+  const int e0 = B == 0, e1 = B == 1, e2 = B == 2;
+  const double lo =
+      ib > 0 ? pml_d1_at<A>(a, p, comp, i0 - e0, i1 - e1, i2 - e2) : 0.0;
+  const double hi = ib < X::N - 1
+                        ? pml_d1_at<A>(a, p, comp, i0 + e0, i1 + e1, i2 + e2)
+                        : 0.0;
+  return (hi - lo) * X::INV2H;
+}
+
+// Dirichlet overwrite: faces in the order axis 0 lower, axis 0 upper, axis 1
+// lower, ... so later faces win on shared edges (constrained_problem.py:286-295)
+template <int A>
+__device__ __forceinline__ double pml_dirichlet_axis(const PmlArgs& a, i64 slot,
+                                                     int comp, int i0, int i1,
+                                                     int i2, double v) {
+  typedef PmlAx<A> X;
+  const int ia = pml_ia<A>(i0, i1, i2);
+  if (((PML_DIR_MASK >> (A * 2)) & 1) && ia == 0) {
+    constexpr int f = A * 2;
+    const double t = __ldg(a.dir[f] + slot * a.dir_stride[f] +
+                           pml_face<A>(i0, i1, i2) * PML_C + comp);
+    if (t == t) v = t;
+  }
+  if (((PML_DIR_MASK >> (A * 2 + 1)) & 1) && ia == X::N - 1) {
+    constexpr int f = A * 2 + 1;
+    const double t = __ldg(a.dir[f] + slot * a.dir_stride[f] +
+                           pml_face<A>(i0, i1, i2) * PML_C + comp);
+    if (t == t) v = t;
+  }
+  return v;
+}
+
+__device__ __forceinline__ double pml_dirichlet(const PmlArgs& a, i64 slot,
+                                                int comp, const PmlCell& c,
+                                                double v) {
+#if PML_DIR_MASK != 0
+  if (PML_NDIM >= 1) v = pml_dirichlet_axis<0>(a, slot, comp, c.i0, c.i1, c.i2, v);
+  if (PML_NDIM >= 2) v = pml_dirichlet_axis<1>(a, slot, comp, c.i0, c.i1, c.i2, v);
+  if (PML_NDIM >= 3) v = pml_dirichlet_axis<2>(a, slot, comp, c.i0, c.i1, c.i2, v);
+#endif
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+// generated right-hand sides (prelude declares, generator defines below)
+// ---------------------------------------------------------------------------
+PML_GENERATED_RHS
+
+// ---------------------------------------------------------------------------
+// stage bodies
+// ---------------------------------------------------------------------------
+enum {
+  PML_FE = 0,     // y+ = c_f(y + dt f(t, y))
+  PML_MID1 = 1,   // u  = c_h(y + (dt/2) f(t, y))
+  PML_MID2 = 2,   // y+ = c_f(y + dt f(t + dt/2, u))
+  PML_RK4_1 = 3,  // K = dt f(t, y);      u = c_h(y + K/2); acc = K
+  PML_RK4_2 = 4,  // K = dt f(t+dt/2, u); u' = c_h(y + K/2); acc += 2K
+  PML_RK4_3 = 5,  // K = dt f(t+dt/2, u); u' = c_f(y + K);   acc += 2K
+  PML_RK4_4 = 6   // K = dt f(t+dt, u);   y+ = c_f(y + (acc + K)/6)
+};
+
+template <int STAGE>
+__device__ __forceinline__ void pml_stage_cell(const PmlArgs& a,
+                                               const PmlCell& c) {
+  constexpr bool first = STAGE == PML_FE || STAGE == PML_MID1 || STAGE == PML_RK4_1;
+  constexpr bool last = STAGE == PML_FE || STAGE == PML_MID2 || STAGE == PML_RK4_4;
+
+  const double* P[PML_C];
+#pragma unroll
+  for (int k = 0; k < PML_C; ++k) {
+    const bool from_y = first || (PML_PASSTHROUGH && PML_KIND[k] != 0);
+    P[k] = (from_y ? a.y : a.u) + (i64)k * PML_NCELLS;
+  }
+
+  double K[PML_NDT > 0 ? PML_NDT : 1];
+  pml_rhs_dt(a, P, c, a.t_eval, K);
+
+#pragma unroll
+  for (int j = 0; j < PML_NDT; ++j) {
+    const int k = PML_DT_IDX[j];
+    const i64 o = (i64)k * PML_NCELLS + c.idx;
+    const double y0 = first ? PML_LD(P[k] + c.idx) : PML_LD(a.y + o);
+    if (STAGE == PML_FE) {
+      a.y_next[o] = pml_dirichlet(a, a.dir_slot, k, c, y0 + a.dt * K[j]);
+    } else if (STAGE == PML_MID1) {
+      a.u_out[o] = pml_dirichlet(a, a.dir_slot, k, c, y0 + (a.dt / 2.0) * K[j]);
+    } else if (STAGE == PML_MID2) {
+      a.y_next[o] = pml_dirichlet(a, a.dir_slot, k, c, y0 + a.dt * K[j]);
+    } else {
+      const double kk = a.dt * K[j];
+      if (STAGE == PML_RK4_1) {
+        a.acc_out[o] = kk;
+        a.u_out[o] = pml_dirichlet(a, a.dir_slot, k, c, y0 + kk / 2.0);
+      } else if (STAGE == PML_RK4_2) {
+        a.acc_out[o] = PML_LD(a.acc_in + o) + 2.0 * kk;
+        a.u_out[o] = pml_dirichlet(a, a.dir_slot, k, c, y0 + kk / 2.0);
+      } else if (STAGE == PML_RK4_3) {
+        a.acc_out[o] = PML_LD(a.acc_in + o) + 2.0 * kk;
+        a.u_out[o] = pml_dirichlet(a, a.dir_slot, k, c, y0 + kk);
+      } else {
+        a.y_next[o] = pml_dirichlet(a, a.dir_slot, k, c,
+                                    y0 + (PML_LD(a.acc_in + o) + kk) / 6.0);
+      }
+    }
+  }
+
+#if PML_NALG + PML_NLAP > 0
+  // non-dt components: their time derivative is zero, so every stage input is
+  // the Dirichlet-constrained step-start value (fdm_operator.py:114-120,
+  // numerical_integrator.py:116-131)
+  if (!last && !PML_PASSTHROUGH) {
+#pragma unroll
+    for (int k = 0; k < PML_C; ++k) {
+      if (PML_KIND[k] == 0) continue;
+      const i64 o = (i64)k * PML_NCELLS + c.idx;
+      a.u_out[o] = pml_dirichlet(a, a.dir_slot, k, c, PML_LD(a.y + o));
+    }
+  }
+  // algebraic (LHS.Y) and Poisson (LHS.Y_LAPLACIAN) right-hand sides use the
+  // step-start time and state (fdm_operator.py:127-161): evaluate them in the
+  // first stage, whose stencil input is exactly that state
+  if (first) {
+    double V[PML_NALG + PML_NLAP];
+    pml_rhs_aux(a, P, c, a.t_eval, V);
+#pragma unroll
+    for (int j = 0; j < PML_NALG; ++j) {
+      const int k = PML_ALG_IDX[j];
+      a.y_next[(i64)k * PML_NCELLS + c.idx] =
+          pml_dirichlet(a, a.dir_slot_full, k, c, V[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < PML_NLAP; ++j)
+      a.lap_rhs[(i64)j * PML_NCELLS + c.idx] = V[PML_NALG + j];
+  }
+#endif
+}
+
+__device__ __forceinline__ bool pml_this_cell(PmlCell& c) {
+#if PML_NDIM <= 1
+  c.i0 = blockIdx.x * PML_BX + threadIdx.x;
+  c.i1 = 0;
+  c.i2 = 0;
+  if (c.i0 >= PML_N0) return false;
+#elif PML_NDIM == 2
+  c.i1 = blockIdx.x * PML_BX + threadIdx.x;
+  c.i0 = blockIdx.y * PML_BY + threadIdx.y;
+  c.i2 = 0;
+  if (c.i1 >= PML_N1 || c.i0 >= PML_N0) return false;
+#else
+  c.i2 = blockIdx.x * PML_BX + threadIdx.x;
+  c.i1 = blockIdx.y * PML_BY + threadIdx.y;
+  c.i0 = blockIdx.z * PML_BZ + threadIdx.z;
+  if (c.i2 >= PML_N2 || c.i1 >= PML_N1 || c.i0 >= PML_N0) return false;
+#endif
+  c.idx = pml_lin(c.i0, c.i1, c.i2);
+  return true;
+}
+
+#define PML_STAGE_KERNEL(NAME, STAGE)                                      \
+  extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ)     \
+      NAME(const __grid_constant__ PmlArgs a) {                            \
+    PmlCell c;                                                             \
+    if (!pml_this_cell(c)) return;                                         \
+    pml_stage_cell<STAGE>(a, c);                                           \
+  }
+
+PML_STAGE_KERNEL(pml_stage_fe, PML_FE)
+PML_STAGE_KERNEL(pml_stage_mid1, PML_MID1)
+PML_STAGE_KERNEL(pml_stage_mid2, PML_MID2)
+PML_STAGE_KERNEL(pml_stage_rk4_1, PML_RK4_1)
+PML_STAGE_KERNEL(pml_stage_rk4_2, PML_RK4_2)
+PML_STAGE_KERNEL(pml_stage_rk4_3, PML_RK4_3)
+PML_STAGE_KERNEL(pml_stage_rk4_4, PML_RK4_4)
+
+// raw right-hand side evaluation (the NumPy-in / NumPy-out differentiator entry
+// points gradient/hessian/divergence/curl/laplacian are served by this kernel)
+extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ)
+    pml_eval_rhs(const __grid_constant__ PmlArgs a) {
+  PmlCell c;
+  if (!pml_this_cell(c)) return;
+  const double* P[PML_C];
+#pragma unroll
+  for (int k = 0; k < PML_C; ++k) P[k] = a.u + (i64)k * PML_NCELLS;
+  double K[PML_NDT > 0 ? PML_NDT : 1];
+  pml_rhs_dt(a, P, c, a.t_eval, K);
+#pragma unroll
+  for (int j = 0; j < PML_NDT; ++j) a.u_out[(i64)j * PML_NCELLS + c.idx] = K[j];
+}
+
+// ---------------------------------------------------------------------------
+// Jacobi anti-Laplacian for the LHS.Y_LAPLACIAN components
+// (numerical_differentiator.py:872-927, 1097-1186).  Component j of the Jacobi
+// state belongs to y component PML_LAP_IDX[j].
+// ---------------------------------------------------------------------------
+#if PML_NLAP > 0
+struct PmlJacobiArgs {
+  PmlArgs base;            // tables; neu_slot / dir_slot are those of t + dt
+  const double* y_hat;     // NLAP planes
+  const double* rhs;       // NLAP planes
+  double* y_new;           // NLAP planes
+  double* partials;        // one partial sum of squares per block
+  const int* done;         // set once ||y_new - y_hat|| <= tol
+};
+
+// start: channels-last (cell, NLAP) host draw -> planes, Dirichlet applied
+extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ)
+    pml_jacobi_init(const __grid_constant__ PmlArgs a,
+                    const double* __restrict__ y_init, double* __restrict__ out) {
+  PmlCell c;
+  if (!pml_this_cell(c)) return;
+#pragma unroll
+  for (int j = 0; j < PML_NLAP; ++j)
+    out[(i64)j * PML_NCELLS + c.idx] = pml_dirichlet(
+        a, a.dir_slot, PML_LAP_IDX[j], c, y_init[c.idx * PML_NLAP + j]);
+}
+
+extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ)
+    pml_jacobi_sweep(const __grid_constant__ PmlJacobiArgs j) {
+  const PmlArgs& a = j.base;
+  if (*(const volatile int*)j.done) return;
+  PmlCell c;
+  const bool active = pml_this_cell(c);
+  double sq = 0.0;
+  if (active) {
+#pragma unroll
+    for (int q = 0; q < PML_NLAP; ++q) {
+      const int comp = PML_LAP_IDX[q];
+      const double* p = j.y_hat + (i64)q * PML_NCELLS;
+      double lo, hi, acc = 0.0;
+#if PML_COORD == 0
+      pml_nb2<0>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
+      acc += (lo + hi) * PML_INVHH0;
+#if PML_NDIM >= 2
+      pml_nb2<1>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
+      acc += (lo + hi) * PML_INVHH1;
+#endif
+#if PML_NDIM >= 3
+      pml_nb2<2>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
+      acc += (lo + hi) * PML_INVHH2;
+#endif
+      acc -= PML_LD(j.rhs + (i64)q * PML_NCELLS + c.idx);
+      const double v = acc * PML_JAC_INV_DIAG;
+#else
+      const double r = __ldg(a.coord[0] + c.i0);
+      const double r2 = r * r;
+      double diag;
+      pml_nb2<0>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
+#if PML_COORD == 3
+      const double s = __ldg(a.aux[1] + c.i2), co = __ldg(a.aux[2] + c.i2);
+      const double r2s2 = r2 * (s * s);
+      acc += (lo + hi) / (PML_H0 * PML_H0) + (hi - lo) / (PML_H0 * r);
+      pml_nb2<1>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
+      acc += ((lo + hi) / (PML_H1 * PML_H1)) / r2s2;
+      pml_nb2<2>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
+      acc += ((lo + hi) / (PML_H2 * PML_H2) +
+              co * (hi - lo) / (2.0 * PML_H2 * s)) / r2;
+      diag = 2.0 / (PML_H0 * PML_H0) + 2.0 / ((PML_H1 * PML_H1) * r2s2) +
+             2.0 / ((PML_H2 * PML_H2) * r2);
+#else
+      acc += (lo + hi) / (PML_H0 * PML_H0) + (hi - lo) / (2.0 * PML_H0 * r);
+      pml_nb2<1>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
+      acc += ((lo + hi) / (PML_H1 * PML_H1)) / r2;
+      diag = 2.0 / (PML_H0 * PML_H0) + 2.0 / ((PML_H1 * PML_H1) * r2);
+#if PML_COORD == 2
+      pml_nb2<2>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
+      acc += (lo + hi) / (PML_H2 * PML_H2);
+      diag += 2.0 / (PML_H2 * PML_H2);
+#endif
+#endif
+      acc -= PML_LD(j.rhs + (i64)q * PML_NCELLS + c.idx);
+      const double v = acc / diag;
+#endif
+      const double vn = pml_dirichlet(a, a.dir_slot, comp, c, v);
+      j.y_new[(i64)q * PML_NCELLS + c.idx] = vn;
+      const double d = vn - PML_LD(p + c.idx);
+      sq += d * d;
+    }
+  }
+  // deterministic block reduction of the squared update norm
+  __shared__ double red[32];
+  const int tid = (threadIdx.z * PML_BY + threadIdx.y) * PML_BX + threadIdx.x;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) sq += __shfl_down_sync(0xffffffffu, sq, off);
+  if ((tid & 31) == 0) red[tid >> 5] = sq;
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+    const int nw = (PML_BX * PML_BY * PML_BZ + 31) / 32;
+    for (int w = 0; w < nw; ++w) s += red[w];
+    const i64 b = ((i64)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    j.partials[b] = s;
+  }
+}
+
+// one block: sums the partials in a fixed order and raises the done flag
+extern "C" __global__ void __launch_bounds__(256)
+    pml_jacobi_check(const double* __restrict__ partials, int n_partials,
+                     double tol, int* done, int* sweeps) {
+  if (*(volatile int*)done) return;
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n_partials; i += 256) s += partials[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if (threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    *sweeps += 1;
+    if (!(sqrt(red[0]) > tol)) *done = 1;
+  }
+}
+
+// final: copies the converged planes into the trajectory slot
+extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ)
+    pml_jacobi_store(const double* __restrict__ y_hat, double* __restrict__ y_next) {
+  PmlCell c;
+  if (!pml_this_cell(c)) return;
+#pragma unroll
+  for (int j = 0; j < PML_NLAP; ++j)
+    y_next[(i64)PML_LAP_IDX[j] * PML_NCELLS + c.idx] =
+        y_hat[(i64)j * PML_NCELLS + c.idx];
+}
+#endif  // PML_NLAP > 0

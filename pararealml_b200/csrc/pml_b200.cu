@@ -1,0 +1,625 @@
+// C-ABI library of the B200-native FDM + Parareal hot path.
+//
+// * plans: NVRTC-compiles the generated stage kernels (fdm_template.cuh behind a
+//   generated prelude) for sm_100a, loads the cubin through the driver API
+//   (entry points fetched with cudaGetDriverEntryPoint, so the library does not
+//   link libcuda and can be dlopen'ed on a machine without a driver) and runs
+//   the device-resident time loop of FDMOperator.solve
+//   (reference fdm_operator.py:48-165, numerical_integrator.py:47-132);
+// * fixed sm_100a kernels: layout conversion and the Parareal state updates
+//   (reference parareal_operator.py:164, 183-185, 85-100, 192).
+//
+// See include/pararealml_b200.h for the contract of every entry point.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <nvrtc.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <vector>
+
+#include "../../include/pararealml_b200.h"
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(const std::string& msg) {
+  g_error = msg;
+  return -1;
+}
+
+#define PML_CUDA(call)                                                       \
+  do {                                                                       \
+    cudaError_t e_ = (call);                                                 \
+    if (e_ != cudaSuccess)                                                   \
+      return fail(std::string(#call) + ": " + cudaGetErrorString(e_));       \
+  } while (0)
+
+// ---- driver API through the runtime (no libcuda link dependency) ----------
+struct Driver {
+  CUresult (*moduleLoadData)(CUmodule*, const void*) = nullptr;
+  CUresult (*moduleUnload)(CUmodule) = nullptr;
+  CUresult (*moduleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+  CUresult (*launchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned,
+                           unsigned, unsigned, unsigned, CUstream, void**,
+                           void**) = nullptr;
+  CUresult (*getErrorString)(CUresult, const char**) = nullptr;
+  bool ready = false;
+};
+Driver g_drv;
+
+int load_driver() {
+  if (g_drv.ready) return 0;
+  PML_CUDA(cudaFree(0));  // makes the primary context current
+  struct {
+    const char* name;
+    void** slot;
+  } syms[] = {
+      {"cuModuleLoadData", (void**)&g_drv.moduleLoadData},
+      {"cuModuleUnload", (void**)&g_drv.moduleUnload},
+      {"cuModuleGetFunction", (void**)&g_drv.moduleGetFunction},
+      {"cuLaunchKernel", (void**)&g_drv.launchKernel},
+      {"cuGetErrorString", (void**)&g_drv.getErrorString},
+  };
+  for (auto& s : syms) {
+    cudaDriverEntryPointQueryResult q;
+    PML_CUDA(cudaGetDriverEntryPoint(s.name, s.slot, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || *s.slot == nullptr)
+      return fail(std::string("driver entry point not found: ") + s.name);
+  }
+  g_drv.ready = true;
+  return 0;
+}
+
+std::string cu_err(CUresult r) {
+  const char* s = nullptr;
+  if (g_drv.getErrorString) g_drv.getErrorString(r, &s);
+  return s ? s : "unknown driver error";
+}
+
+#define PML_CU(call)                                                         \
+  do {                                                                       \
+    CUresult r_ = (call);                                                    \
+    if (r_ != CUDA_SUCCESS) return fail(std::string(#call) + ": " + cu_err(r_)); \
+  } while (0)
+
+// mirror of PmlArgs in fdm_template.cuh (kept layout-identical)
+struct PmlArgs {
+  const double* u;
+  const double* y;
+  const double* acc_in;
+  double* u_out;
+  double* acc_out;
+  double* y_next;
+  double* lap_rhs;
+  double t_eval;
+  double dt;
+  long long neu_slot;
+  long long dir_slot;
+  long long dir_slot_full;
+  const double* neu[6];
+  long long neu_stride[6];
+  const double* dir[6];
+  long long dir_stride[6];
+  const double* coord[3];
+  const double* aux[4];
+};
+
+struct PmlJacobiArgs {
+  PmlArgs base;
+  const double* y_hat;
+  const double* rhs;
+  double* y_new;
+  double* partials;
+  const int* done;
+};
+
+int nvrtc_compile(const char* source, std::vector<char>& cubin) {
+  nvrtcProgram prog;
+  if (nvrtcCreateProgram(&prog, source, "pml_generated.cu", 0, nullptr,
+                         nullptr) != NVRTC_SUCCESS)
+    return fail("nvrtcCreateProgram failed");
+  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17",
+                        "-lineinfo", "--fmad=true"};
+  nvrtcResult r = nvrtcCompileProgram(prog, 4, opts);
+  if (r != NVRTC_SUCCESS) {
+    size_t n = 0;
+    nvrtcGetProgramLogSize(prog, &n);
+    std::string log(n, '\0');
+    nvrtcGetProgramLog(prog, &log[0]);
+    nvrtcDestroyProgram(&prog);
+    return fail(std::string("NVRTC: ") + nvrtcGetErrorString(r) + "\n" + log);
+  }
+  size_t n = 0;
+  if (nvrtcGetCUBINSize(prog, &n) != NVRTC_SUCCESS || n == 0) {
+    nvrtcDestroyProgram(&prog);
+    return fail("NVRTC produced no cubin");
+  }
+  cubin.resize(n);
+  nvrtcGetCUBIN(prog, cubin.data());
+  nvrtcDestroyProgram(&prog);
+  return 0;
+}
+
+bool read_file(const char* path, std::vector<char>& out) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) return false;
+  out.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
+  return !out.empty();
+}
+
+bool write_file(const char* path, const std::vector<char>& data) {
+  std::string tmp = std::string(path) + ".tmp";
+  {
+    std::ofstream f(tmp, std::ios::binary);
+    if (!f) return false;
+    f.write(data.data(), (std::streamsize)data.size());
+  }
+  return std::rename(tmp.c_str(), path) == 0;
+}
+
+}  // namespace
+
+struct pml_plan {
+  pml_plan_desc desc;
+  CUmodule module = nullptr;
+  CUfunction stage[7] = {};
+  CUfunction eval_rhs = nullptr;
+  CUfunction jac_init = nullptr, jac_sweep = nullptr, jac_check = nullptr,
+             jac_store = nullptr;
+  pml_tables tables{};
+  dim3 grid, block;
+  long long n_cells = 0;
+  long long n_blocks = 0;
+  long long launches = 0;
+};
+
+namespace {
+
+void fill_tables(const pml_plan* p, PmlArgs& a) {
+  for (int f = 0; f < 6; ++f) {
+    a.neu[f] = p->tables.neu[f];
+    a.neu_stride[f] = p->tables.neu_stride[f];
+    a.dir[f] = p->tables.dir[f];
+    a.dir_stride[f] = p->tables.dir_stride[f];
+  }
+  for (int i = 0; i < 3; ++i) a.coord[i] = p->tables.coord[i];
+  for (int i = 0; i < 4; ++i) a.aux[i] = p->tables.aux[i];
+}
+
+int launch(pml_plan* p, CUfunction fn, void** params, CUstream s) {
+  PML_CU(g_drv.launchKernel(fn, p->grid.x, p->grid.y, p->grid.z, p->block.x,
+                            p->block.y, p->block.z, 0, s, params, nullptr));
+  p->launches += 1;
+  return 0;
+}
+
+int jacobi_solve(pml_plan* p, const pml_workspace* ws, const PmlArgs& tbl,
+                 const double* rhs, const double* y_init, double* y_next,
+                 double tol, long long max_sweeps, int* sweeps_out,
+                 CUstream s) {
+  // tbl carries the slots of t + dt for both Neumann and Dirichlet tables
+  PML_CUDA(cudaMemsetAsync(ws->flags, 0, 2 * sizeof(int), (cudaStream_t)s));
+  {
+    PmlArgs a = tbl;
+    const double* init = y_init;
+    double* out = ws->jac_a;
+    void* params[] = {&a, &init, &out};
+    if (launch(p, p->jac_init, params, s)) return -1;
+  }
+  double* bufs[2] = {ws->jac_a, ws->jac_b};
+  long long issued = 0;
+  int host_flags[2] = {0, 0};
+  long long batch = 16;
+  int n_partials = (int)p->n_blocks;
+  while (true) {
+    long long todo = batch;
+    if (max_sweeps > 0 && issued + todo > max_sweeps) todo = max_sweeps - issued;
+    if (todo <= 0) break;
+    for (long long k = 0; k < todo; ++k, ++issued) {
+      PmlJacobiArgs j;
+      j.base = tbl;
+      j.y_hat = bufs[issued & 1];
+      j.rhs = rhs;
+      j.y_new = bufs[(issued + 1) & 1];
+      j.partials = ws->partials;
+      j.done = ws->flags;
+      void* params[] = {&j};
+      if (launch(p, p->jac_sweep, params, s)) return -1;
+      const double* partials = ws->partials;
+      int* done = ws->flags;
+      int* sweeps = ws->flags + 1;
+      void* cparams[] = {&partials, &n_partials, &tol, &done, &sweeps};
+      PML_CU(g_drv.launchKernel(p->jac_check, 1, 1, 1, 256, 1, 1, 0, s, cparams,
+                                nullptr));
+      p->launches += 1;
+    }
+    PML_CUDA(cudaMemcpyAsync(host_flags, ws->flags, 2 * sizeof(int),
+                             cudaMemcpyDeviceToHost, (cudaStream_t)s));
+    PML_CUDA(cudaStreamSynchronize((cudaStream_t)s));
+    if (host_flags[0]) break;
+    if (batch < 4096) batch *= 2;
+  }
+  const long long sweeps = host_flags[1];
+  if (sweeps_out) *sweeps_out = (int)sweeps;
+  const double* result = bufs[sweeps & 1];
+  void* params[] = {&result, &y_next};
+  return launch(p, p->jac_store, params, s);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pml_last_error(void) { return g_error.c_str(); }
+
+int pml_version(void) { return 100; }
+
+int pml_compile_to_cubin(const char* source, const char* cubin_path) {
+  std::vector<char> cubin;
+  if (nvrtc_compile(source, cubin)) return -1;
+  if (!write_file(cubin_path, cubin))
+    return fail(std::string("cannot write ") + cubin_path);
+  return 0;
+}
+
+int pml_plan_create(const char* source, const pml_plan_desc* desc,
+                    const char* cubin_path, pml_plan** out) {
+  if (!source || !desc || !out) return fail("null argument");
+  if (load_driver()) return -1;
+  std::vector<char> cubin;
+  bool cached = cubin_path && read_file(cubin_path, cubin);
+  if (!cached) {
+    if (nvrtc_compile(source, cubin)) return -1;
+    if (cubin_path) write_file(cubin_path, cubin);
+  }
+  pml_plan* p = new pml_plan();
+  p->desc = *desc;
+  CUresult r = g_drv.moduleLoadData(&p->module, cubin.data());
+  if (r != CUDA_SUCCESS && cached) {
+    // stale cache entry: recompile
+    if (nvrtc_compile(source, cubin)) { delete p; return -1; }
+    write_file(cubin_path, cubin);
+    r = g_drv.moduleLoadData(&p->module, cubin.data());
+  }
+  if (r != CUDA_SUCCESS) {
+    delete p;
+    return fail("cuModuleLoadData: " + cu_err(r));
+  }
+  static const char* names[7] = {"pml_stage_fe",    "pml_stage_mid1",
+                                 "pml_stage_mid2",  "pml_stage_rk4_1",
+                                 "pml_stage_rk4_2", "pml_stage_rk4_3",
+                                 "pml_stage_rk4_4"};
+  for (int i = 0; i < 7; ++i) {
+    r = g_drv.moduleGetFunction(&p->stage[i], p->module, names[i]);
+    if (r != CUDA_SUCCESS) {
+      std::string m = std::string("missing kernel ") + names[i];
+      pml_plan_destroy(p);
+      return fail(m);
+    }
+  }
+  r = g_drv.moduleGetFunction(&p->eval_rhs, p->module, "pml_eval_rhs");
+  if (r != CUDA_SUCCESS) {
+    pml_plan_destroy(p);
+    return fail("missing kernel pml_eval_rhs");
+  }
+  if (desc->n_lap > 0) {
+    struct { const char* n; CUfunction* f; } js[] = {
+        {"pml_jacobi_init", &p->jac_init}, {"pml_jacobi_sweep", &p->jac_sweep},
+        {"pml_jacobi_check", &p->jac_check}, {"pml_jacobi_store", &p->jac_store}};
+    for (auto& j : js) {
+      r = g_drv.moduleGetFunction(j.f, p->module, j.n);
+      if (r != CUDA_SUCCESS) {
+        std::string m = std::string("missing kernel ") + j.n;
+        pml_plan_destroy(p);
+        return fail(m);
+      }
+    }
+  }
+  const int* n = desc->shape;
+  const int* b = desc->block;
+  p->block = dim3(b[0], b[1], b[2]);
+  auto cdiv = [](int a, int d) { return (unsigned)((a + d - 1) / d); };
+  if (desc->n_dims <= 1)
+    p->grid = dim3(cdiv(n[0], b[0]), 1, 1);
+  else if (desc->n_dims == 2)
+    p->grid = dim3(cdiv(n[1], b[0]), cdiv(n[0], b[1]), 1);
+  else
+    p->grid = dim3(cdiv(n[2], b[0]), cdiv(n[1], b[1]), cdiv(n[0], b[2]));
+  p->n_cells = (long long)n[0] * n[1] * n[2];
+  p->n_blocks = (long long)p->grid.x * p->grid.y * p->grid.z;
+  *out = p;
+  return 0;
+}
+
+int pml_plan_destroy(pml_plan* p) {
+  if (!p) return 0;
+  if (p->module && g_drv.moduleUnload) g_drv.moduleUnload(p->module);
+  delete p;
+  return 0;
+}
+
+int pml_plan_set_tables(pml_plan* p, const pml_tables* t) {
+  if (!p || !t) return fail("null argument");
+  p->tables = *t;
+  return 0;
+}
+
+long long pml_plan_launches(const pml_plan* p) { return p ? p->launches : 0; }
+
+int pml_fdm_run(pml_plan* p, int integrator, const pml_workspace* ws,
+                const double* y0, double* traj, long long stride,
+                const double* t_host, int n_steps, double d_t, long long slot0,
+                const double* jacobi_init, double jacobi_tol,
+                long long max_sweeps, int* sweeps_out, void* stream) {
+  if (!p || !ws || !y0 || !traj || !t_host) return fail("null argument");
+  if (integrator < 0 || integrator > 2) return fail("unknown integrator");
+  if (p->desc.n_lap > 0 && !jacobi_init)
+    return fail("Y_LAPLACIAN equations need a Jacobi start array");
+  CUstream s = (CUstream)stream;
+  PmlArgs a;
+  std::memset(&a, 0, sizeof(a));
+  fill_tables(p, a);
+  a.dt = d_t;
+  a.lap_rhs = ws->lap_rhs;
+  const double half = d_t / 2.0;
+  const long long lap_elems = (long long)p->desc.n_lap * p->n_cells;
+  for (int j = 0; j < n_steps; ++j) {
+    const double t = t_host[j];
+    const double* y = j == 0 ? y0 : traj + (long long)(j - 1) * stride;
+    double* y_next = traj + (long long)j * stride;
+    const long long s_t = slot0 + 3LL * j, s_h = s_t + 1, s_f = s_t + 2;
+    a.y = y;
+    a.y_next = y_next;
+    a.dir_slot_full = s_f;
+    void* params[] = {&a};
+    auto stage = [&](int k, const double* u, double* u_out, double t_eval,
+                     long long neu_slot, long long dir_slot) {
+      a.u = u;
+      a.u_out = u_out;
+      a.acc_in = ws->acc;
+      a.acc_out = ws->acc;
+      a.t_eval = t_eval;
+      a.neu_slot = neu_slot;
+      a.dir_slot = dir_slot;
+      return launch(p, p->stage[k], params, s);
+    };
+    int rc = 0;
+    if (integrator == PML_INTEGRATOR_FORWARD_EULER) {
+      rc = stage(0, y, nullptr, t, s_t, s_f);
+    } else if (integrator == PML_INTEGRATOR_EXPLICIT_MIDPOINT) {
+      rc = stage(1, y, ws->u_a, t, s_t, s_h);
+      if (!rc) rc = stage(2, ws->u_a, nullptr, t + half, s_h, s_f);
+    } else {
+      rc = stage(3, y, ws->u_a, t, s_t, s_h);
+      if (!rc) rc = stage(4, ws->u_a, ws->u_b, t + half, s_h, s_h);
+      if (!rc) rc = stage(5, ws->u_b, ws->u_a, t + half, s_h, s_f);
+      if (!rc) rc = stage(6, ws->u_a, nullptr, t + d_t, s_f, s_f);
+    }
+    if (rc) return rc;
+    if (p->desc.n_lap > 0) {
+      PmlArgs tbl = a;
+      tbl.neu_slot = s_f;
+      tbl.dir_slot = s_f;
+      int sweeps = 0;
+      if (jacobi_solve(p, ws, tbl, ws->lap_rhs, jacobi_init + (long long)j * lap_elems,
+                       y_next, jacobi_tol, max_sweeps, &sweeps, s))
+        return -1;
+      if (sweeps_out) sweeps_out[j] = sweeps;
+    }
+  }
+  return 0;
+}
+
+int pml_eval_rhs(pml_plan* p, const double* u, double* out, double t,
+                 long long slot, void* stream) {
+  if (!p || !u || !out) return fail("null argument");
+  PmlArgs a;
+  std::memset(&a, 0, sizeof(a));
+  fill_tables(p, a);
+  a.u = u;
+  a.y = u;
+  a.u_out = out;
+  a.t_eval = t;
+  a.neu_slot = slot;
+  a.dir_slot = slot;
+  a.dir_slot_full = slot;
+  void* params[] = {&a};
+  return launch(p, p->eval_rhs, params, (CUstream)stream);
+}
+
+int pml_jacobi_run(pml_plan* p, const pml_workspace* ws, const double* rhs,
+                   const double* y_init, double* y_next, long long slot,
+                   double tol, long long max_sweeps, int* sweeps_out,
+                   void* stream) {
+  if (!p || !ws || !rhs || !y_init || !y_next) return fail("null argument");
+  if (p->desc.n_lap <= 0) return fail("plan has no Y_LAPLACIAN equations");
+  PmlArgs a;
+  std::memset(&a, 0, sizeof(a));
+  fill_tables(p, a);
+  a.neu_slot = slot;
+  a.dir_slot = slot;
+  a.dir_slot_full = slot;
+  return jacobi_solve(p, ws, a, rhs, y_init, y_next, tol, max_sweeps,
+                      sweeps_out, (CUstream)stream);
+}
+
+}  // extern "C"
+
+// ===========================================================================
+// fixed sm_100a kernels
+// ===========================================================================
+namespace {
+
+constexpr int kThreads = 256;
+
+// (state, cell, comp) channels-last  <->  (state, comp, cell) planes.  Reads and
+// writes are both coalesced: consecutive threads walk the contiguous side and
+// the strided side stays within y_dim * 8 bytes of each other (L1/L2 merge).
+__global__ void __launch_bounds__(kThreads)
+aos_to_soa_kernel(const double* __restrict__ aos, double* __restrict__ soa,
+                  long long n_cells, int c_dim, long long total) {
+  for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < total;
+       i += (long long)gridDim.x * kThreads) {
+    const long long per_state = n_cells * c_dim;
+    const long long st = i / per_state, r = i - st * per_state;
+    const long long c = r / n_cells, cell = r - c * n_cells;
+    soa[i] = __ldg(aos + st * per_state + cell * c_dim + c);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+soa_to_aos_kernel(const double* __restrict__ soa, double* __restrict__ aos,
+                  long long n_cells, int c_dim, long long total) {
+  for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < total;
+       i += (long long)gridDim.x * kThreads) {
+    const long long per_state = n_cells * c_dim;
+    const long long st = i / per_state, r = i - st * per_state;
+    const long long cell = r / c_dim, c = r - cell * c_dim;
+    aos[i] = __ldg(soa + st * per_state + c * n_cells + cell);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+correction_kernel(const double* __restrict__ f, const double* __restrict__ g,
+                  double* __restrict__ corr, long long n) {
+  for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < n;
+       i += (long long)gridDim.x * kThreads)
+    corr[i] = __ldg(f + i) - __ldg(g + i);
+}
+
+// new = g + corr and per-block partial sums of (new - old)^2 per component
+__global__ void __launch_bounds__(kThreads)
+update_kernel(const double* __restrict__ g, const double* __restrict__ corr,
+              const double* __restrict__ old_end, double* __restrict__ new_end,
+              double* __restrict__ partials, long long n_cells) {
+  const int c = blockIdx.y;
+  const long long base = (long long)c * n_cells;
+  double sq = 0.0;
+  for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < n_cells;
+       i += (long long)gridDim.x * kThreads) {
+    const double v = __ldg(g + base + i) + __ldg(corr + base + i);
+    const double d = v - __ldg(old_end + base + i);
+    new_end[base + i] = v;
+    sq += d * d;
+  }
+  __shared__ double red[kThreads / 32];
+  for (int off = 16; off > 0; off >>= 1) sq += __shfl_down_sync(0xffffffffu, sq, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) s += red[w];
+    partials[(long long)c * gridDim.x + blockIdx.x] = s;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+finish_sumsq_kernel(const double* __restrict__ partials, int n_partials,
+                    double* __restrict__ sumsq) {
+  const int c = blockIdx.x;
+  __shared__ double red[kThreads];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n_partials; i += kThreads)
+    s += partials[(long long)c * n_partials + i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int off = kThreads / 2; off > 0; off >>= 1) {
+    if (threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) sumsq[c] = red[0];
+}
+
+__global__ void __launch_bounds__(kThreads)
+delta_kernel(const double* __restrict__ new_end, const double* __restrict__ last,
+             double* __restrict__ delta, long long n) {
+  for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < n;
+       i += (long long)gridDim.x * kThreads)
+    delta[i] = __ldg(new_end + i) - __ldg(last + i);
+}
+
+__global__ void __launch_bounds__(kThreads)
+shift_kernel(double* __restrict__ traj, long long n_steps, long long stride,
+             const double* __restrict__ delta, long long n) {
+  const long long step = blockIdx.y;
+  double* row = traj + step * stride;
+  for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < n;
+       i += (long long)gridDim.x * kThreads)
+    row[i] += __ldg(delta + i);
+  (void)n_steps;
+}
+
+unsigned grid_for(long long n, unsigned cap = 148 * 16) {
+  long long b = (n + kThreads - 1) / kThreads;
+  if (b < 1) b = 1;
+  return (unsigned)(b < cap ? b : cap);
+}
+
+}  // namespace
+
+extern "C" {
+
+int pml_aos_to_soa(const double* aos, double* soa, long long n_cells, int y_dim,
+                   long long n_states, void* stream) {
+  const long long total = n_cells * y_dim * n_states;
+  if (total == 0) return 0;
+  aos_to_soa_kernel<<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(
+      aos, soa, n_cells, y_dim, total);
+  PML_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int pml_soa_to_aos(const double* soa, double* aos, long long n_cells, int y_dim,
+                   long long n_states, void* stream) {
+  const long long total = n_cells * y_dim * n_states;
+  if (total == 0) return 0;
+  soa_to_aos_kernel<<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(
+      soa, aos, n_cells, y_dim, total);
+  PML_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int pml_parareal_correction(const double* f, const double* g, double* corr,
+                            long long n, void* stream) {
+  correction_kernel<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(f, g, corr, n);
+  PML_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int pml_parareal_update(const double* g, const double* corr, const double* old_end,
+                        double* new_end, double* sumsq, double* scratch,
+                        long long n_cells, int y_dim, void* stream) {
+  unsigned blocks = grid_for(n_cells, 1024);
+  dim3 grid(blocks, (unsigned)y_dim);
+  update_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(g, corr, old_end, new_end,
+                                                             scratch, n_cells);
+  PML_CUDA(cudaGetLastError());
+  finish_sumsq_kernel<<<(unsigned)y_dim, kThreads, 0, (cudaStream_t)stream>>>(
+      scratch, (int)blocks, sumsq);
+  PML_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int pml_parareal_shift(double* traj, long long n_steps, long long stride,
+                       const double* new_end, double* delta, long long n,
+                       void* stream) {
+  if (n_steps <= 0) return 0;
+  delta_kernel<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(
+      new_end, traj + (n_steps - 1) * stride, delta, n);
+  PML_CUDA(cudaGetLastError());
+  for (long long first = 0; first < n_steps; first += 32768) {
+    const long long count = n_steps - first < 32768 ? n_steps - first : 32768;
+    dim3 grid(grid_for(n, 148 * 4), (unsigned)count);
+    shift_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+        traj + first * stride, count, stride, delta, n);
+    PML_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // extern "C"

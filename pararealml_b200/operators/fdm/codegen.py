@@ -1,0 +1,459 @@
+"""SymPy system -> CUDA C prelude for the fixed stage-kernel template.
+
+Replaces the reference's per-symbol NumPy evaluators and ``sp.lambdify``
+(``operators/symbol_mapper.py:160-253``, ``operators/fdm/fdm_symbol_mapper.py
+:45-158``): every free symbol of the right-hand sides becomes an inline
+expression over the template's stencil primitives (``pml_d1_at``,
+``pml_d2_at``, ``pml_d2m_at``; csrc/fdm_template.cuh), with the coordinate
+system algebra of ``numerical_differentiator.py:114-870`` written out, and the
+right-hand sides themselves are printed with SymPy's C printer.  Nothing is
+lambdified to NumPy.
+"""
+import hashlib
+import os
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import sympy as sp
+from sympy.printing.c import C99CodePrinter
+
+TEMPLATE_PATH = os.path.join(
+    os.path.dirname(os.path.abspath(__file__)), "..", "..", "csrc",
+    "fdm_template.cuh",
+)
+
+COORD_CODES = {"CARTESIAN": 0, "POLAR": 1, "CYLINDRICAL": 2, "SPHERICAL": 3}
+KIND_CODES = {"D_Y_OVER_D_T": 0, "Y": 1, "Y_LAPLACIAN": 2}
+
+
+def c_double(v: float) -> str:
+    """Exact C literal of a double (hex float keeps every bit)."""
+    v = float(v)
+    if v != v:
+        return "PML_NAN"
+    if v in (float("inf"), float("-inf")):
+        raise ValueError("infinite constant")
+    return f"({v.hex()})"
+
+
+class _CudaPrinter(C99CodePrinter):
+    """C printer with exact constants and multiplication chains for small
+    integer powers (``pow`` is two orders of magnitude slower in fp64)."""
+
+    def __init__(self, names: Dict[str, str]):
+        super().__init__({"allow_unknown_functions": False})
+        self._names = names
+
+    def _print_Symbol(self, expr):
+        return self._names[expr.name]
+
+    def _print_Float(self, expr):
+        return c_double(float(expr))
+
+    def _print_Integer(self, expr):
+        return f"{int(expr)}.0"
+
+    def _print_Rational(self, expr):
+        return f"({int(expr.p)}.0/{int(expr.q)}.0)"
+
+    def _print_Pow(self, expr):
+        base, exp = expr.base, expr.exp
+        if exp.is_Integer and 1 <= abs(int(exp)) <= 8:
+            b = self._print(base)
+            chain = "*".join([f"({b})"] * abs(int(exp)))
+            return f"({chain})" if int(exp) > 0 else f"(1.0/({chain}))"
+        if exp == sp.Rational(1, 2):
+            return f"sqrt({self._print(base)})"
+        if exp == sp.Rational(-1, 2):
+            return f"(1.0/sqrt({self._print(base)}))"
+        return f"pow({self._print(base)}, {self._print(exp)})"
+
+
+@dataclass
+class ProblemSpec:
+    """Everything the generated kernels are specialised on."""
+
+    shape: Tuple[int, ...]  # mesh vertices shape, () for an ODE
+    d_x: Tuple[float, ...]
+    coord: str  # CARTESIAN | POLAR | CYLINDRICAL | SPHERICAL
+    y_dim: int
+    rhs: Sequence[sp.Expr]
+    kinds: Sequence[str]  # LHS kind name per equation
+    neu_mask: int = 0  # bit (axis * 2 + side): a Neumann table exists
+    dir_mask: int = 0
+    passthrough: bool = False
+    coherent_loads: bool = False
+    eval_only: bool = False  # the differentiator entry points
+    block: Optional[Tuple[int, int, int]] = None
+
+
+def default_block(shape) -> Tuple[int, int, int]:
+    nd = len(shape)
+    if nd <= 1:
+        return (256, 1, 1)
+    if nd == 2:
+        return (128, 2, 1) if shape[1] >= 128 else (32, 8, 1)
+    if shape[2] >= 64:
+        return (64, 2, 2)
+    return (32, 4, 2) if shape[2] >= 32 else (16, 4, 4)
+
+
+class _LeafBuilder:
+    """Turns symbol names into C expressions and records the stencil
+    primitives they need (emitted once each)."""
+
+    def __init__(self, spec: ProblemSpec):
+        self.spec = spec
+        self.nd = len(spec.shape)
+        self.cs = spec.coord
+        self.prims: Dict[str, str] = {}
+        self.order: List[str] = []
+
+    def _prim(self, name: str, code: str) -> str:
+        if name not in self.prims:
+            self.prims[name] = code
+            self.order.append(name)
+        return name
+
+    # primitives ----------------------------------------------------------
+    def Y(self, c):
+        return self._prim(f"Y{c}", f"PML_LD(P[{c}] + c.idx)")
+
+    def D1(self, c, a):
+        return self._prim(
+            f"D1_{c}_{a}", f"pml_d1_at<{a}>(a, P[{c}], {c}, c.i0, c.i1, c.i2)"
+        )
+
+    def D2(self, c, a, b=None):
+        if b is None or a == b:
+            return self._prim(
+                f"D2_{c}_{a}",
+                f"pml_d2_at<{a}>(a, P[{c}], {c}, c.i0, c.i1, c.i2)",
+            )
+        return self._prim(
+            f"D2M_{c}_{a}_{b}",
+            f"pml_d2m_at<{a}, {b}>(a, P[{c}], {c}, c.i0, c.i1, c.i2)",
+        )
+
+    def X(self, a):
+        return self._prim(f"X{a}", f"__ldg(a.coord[{a}] + c.i{a})")
+
+    def IR(self):
+        return self._prim("IR", "__ldg(a.aux[0] + c.i0)")
+
+    def SIN(self):
+        return self._prim("SINP", "__ldg(a.aux[1] + c.i2)")
+
+    def COS(self):
+        return self._prim("COSP", "__ldg(a.aux[2] + c.i2)")
+
+    def IS(self):
+        return self._prim("ISINP", "__ldg(a.aux[3] + c.i2)")
+
+    def IRS(self):
+        return self._prim("IRS", f"({self.IR()} * {self.IS()})")
+
+    # leaves (numerical_differentiator.py:114-870) --------------------------
+    def _check_axis(self, a):
+        if not 0 <= a < self.nd:
+            raise ValueError(f"x axis {a} out of range for {self.nd} dims")
+
+    def gradient(self, c, a):
+        self._check_axis(a)
+        d = self.D1(c, a)
+        if self.cs == "CARTESIAN":
+            return d
+        if self.cs == "SPHERICAL":
+            if a == 0:
+                return d
+            return f"({d} * {self.IRS()})" if a == 1 else f"({d} * {self.IR()})"
+        return f"({d} * {self.IR()})" if a == 1 else d
+
+    def hessian(self, c, a, b):
+        self._check_axis(a)
+        self._check_axis(b)
+        d2 = self.D2(c, a, b)
+        cs = self.cs
+        if cs == "CARTESIAN":
+            return d2
+        ir = self.IR()
+        axes = {a, b}
+        if cs == "SPHERICAL":
+            if a == 0 and b == 0:
+                return d2
+            if a == 1 and b == 1:
+                return (
+                    f"(({self.D1(c, 0)} + ({d2} * {self.IS()} + {self.COS()} * "
+                    f"{self.D1(c, 2)}) * {self.IRS()}) * {ir})"
+                )
+            if a == 2 and b == 2:
+                return f"(({d2} * {ir} + {self.D1(c, 0)}) * {ir})"
+            if axes == {0, 1}:
+                return f"(({d2} - {self.D1(c, 1)} * {ir}) * {self.IRS()})"
+            if axes == {0, 2}:
+                return f"(({d2} - {self.D1(c, 2)} * {ir}) * {ir})"
+            return (
+                f"(({self.SIN()} * {d2} - {self.COS()} * {self.D1(c, 1)}) * "
+                f"({self.IRS()} * {self.IRS()}))"
+            )
+        if a != 1 and b != 1:
+            return d2
+        if a == 1 and b == 1:
+            return f"(({d2} * {ir} + {self.D1(c, 0)}) * {ir})"
+        if axes == {0, 1}:
+            return f"(({d2} - {self.D1(c, 1)} * {ir}) * {ir})"
+        return f"({d2} * {ir})"
+
+    def divergence(self, comps):
+        if len(comps) != self.nd:
+            raise ValueError("divergence needs one component per axis")
+        cs = self.cs
+        if cs == "CARTESIAN":
+            return "(" + " + ".join(self.D1(c, i) for i, c in enumerate(comps)) + ")"
+        ir = self.IR()
+        if cs == "SPHERICAL":
+            return (
+                f"({self.D1(comps[0], 0)} + ({self.D1(comps[2], 2)} + 2.0 * "
+                f"{self.Y(comps[0])} + ({self.D1(comps[1], 1)} + {self.COS()} * "
+                f"{self.Y(comps[2])}) * {self.IS()}) * {ir})"
+            )
+        out = (
+            f"({self.D1(comps[0], 0)} + ({self.Y(comps[0])} + "
+            f"{self.D1(comps[1], 1)}) * {ir})"
+        )
+        if cs == "CYLINDRICAL":
+            out = f"({out} + {self.D1(comps[2], 2)})"
+        return out
+
+    def curl(self, comps, ind):
+        nd = self.nd
+        if not 2 <= nd <= 3:
+            raise ValueError("curl needs 2 or 3 spatial dimensions")
+        if len(comps) != nd:
+            raise ValueError("curl needs one component per axis")
+        if nd == 2 and ind != 0:
+            raise ValueError("2D curl only has component 0")
+        if not 0 <= ind < nd:
+            raise ValueError(f"curl index {ind} out of range")
+        v = comps
+        cs = self.cs
+        if cs == "CARTESIAN":
+            if nd == 2 or ind == 2:
+                return f"({self.D1(v[1], 0)} - {self.D1(v[0], 1)})"
+            if ind == 0:
+                return f"({self.D1(v[2], 1)} - {self.D1(v[1], 2)})"
+            return f"({self.D1(v[0], 2)} - {self.D1(v[2], 0)})"
+        ir = self.IR()
+        if cs == "SPHERICAL":
+            if ind == 0:
+                return (
+                    f"(({self.D1(v[1], 2)} + ({self.COS()} * {self.Y(v[1])} - "
+                    f"{self.D1(v[2], 1)}) * {self.IS()}) * {ir})"
+                )
+            if ind == 1:
+                return (
+                    f"({self.D1(v[2], 0)} + ({self.Y(v[2])} - "
+                    f"{self.D1(v[0], 2)}) * {ir})"
+                )
+            return (
+                f"(-{self.D1(v[1], 0)} + ({self.D1(v[0], 1)} * {self.IS()} - "
+                f"{self.Y(v[1])}) * {ir})"
+            )
+        if cs == "POLAR" or ind == 2:
+            return (
+                f"({self.D1(v[1], 0)} + ({self.Y(v[1])} - {self.D1(v[0], 1)}) "
+                f"* {ir})"
+            )
+        if ind == 0:
+            return f"({self.D1(v[2], 1)} * {ir} - {self.D1(v[1], 2)})"
+        return f"({self.D1(v[0], 2)} - {self.D1(v[2], 0)})"
+
+    def laplacian(self, c):
+        cs = self.cs
+        if cs == "CARTESIAN":
+            return "(" + " + ".join(self.D2(c, a) for a in range(self.nd)) + ")"
+        ir = self.IR()
+        if cs == "SPHERICAL":
+            return (
+                f"({self.D2(c, 0)} + (2.0 * {self.D1(c, 0)} + ({self.D2(c, 2)} "
+                f"+ ({self.COS()} * {self.D1(c, 2)} + {self.D2(c, 1)} * "
+                f"{self.IS()}) * {self.IS()}) * {ir}) * {ir})"
+            )
+        out = (
+            f"({self.D2(c, 0)} + ({self.D2(c, 1)} * {ir} + {self.D1(c, 0)}) "
+            f"* {ir})"
+        )
+        if cs == "CYLINDRICAL":
+            out = f"({out} + {self.D2(c, 2)})"
+        return out
+
+    def vector_laplacian(self, comps, ind):
+        if len(comps) != self.nd:
+            raise ValueError("vector Laplacian needs one component per axis")
+        if not 0 <= ind < self.nd:
+            raise ValueError(f"vector Laplacian index {ind} out of range")
+        v = comps
+        lap = self.laplacian(v[ind])
+        cs = self.cs
+        if cs == "CARTESIAN":
+            return lap
+        ir2 = f"({self.IR()} * {self.IR()})"
+        if cs == "SPHERICAL":
+            if ind == 1:
+                return (
+                    f"({lap} - 2.0 * ({self.Y(v[0])} + {self.D1(v[2], 2)} + "
+                    f"({self.COS()} * {self.Y(v[2])} + {self.D1(v[1], 1)}) * "
+                    f"{self.IS()}) * {ir2})"
+                )
+            if ind == 2:
+                return (
+                    f"({lap} + 2.0 * ({self.D1(v[0], 1)} + ({self.COS()} * "
+                    f"{self.D1(v[2], 1)} - {self.Y(v[1])} / 2.0) * {self.IS()}) "
+                    f"* ({self.IS()} * {ir2}))"
+                )
+            return (
+                f"({lap} + 2.0 * ({self.D1(v[0], 2)} - ({self.Y(v[2])} / 2.0 + "
+                f"{self.COS()} * {self.D1(v[1], 1)}) * ({self.IS()} * "
+                f"{self.IS()})) * {ir2})"
+            )
+        if ind == 0:
+            return (
+                f"({lap} - ({self.Y(v[0])} + 2.0 * {self.D1(v[1], 1)}) * {ir2})"
+            )
+        if ind == 1:
+            return (
+                f"({lap} - ({self.Y(v[1])} - 2.0 * {self.D1(v[0], 1)}) * {ir2})"
+            )
+        return lap
+
+    # symbol name -> expression --------------------------------------------
+    def leaf(self, name: str) -> str:
+        tokens = name.split("_")
+        kind = tokens[0]
+        idx = [int(s) for s in tokens[1:]]
+        if kind == "t":
+            return "t"
+        if kind == "y":
+            return self.Y(idx[0])
+        if kind == "x":
+            self._check_axis(idx[0])
+            return self.X(idx[0])
+        if kind == "y-gradient":
+            return self.gradient(*idx)
+        if kind == "y-hessian":
+            return self.hessian(*idx)
+        if kind == "y-laplacian":
+            return self.laplacian(idx[0])
+        if kind == "y-divergence":
+            return self.divergence(idx)
+        if kind == "y-curl":
+            if self.nd == 2:
+                return self.curl(idx, 0)
+            return self.curl(idx[:-1], idx[-1])
+        if kind == "y-vector-laplacian":
+            return self.vector_laplacian(idx[:-1], idx[-1])
+        raise KeyError(name)
+
+
+def _emit_function(fn_name: str, spec: ProblemSpec, eq_indices: Sequence[int]):
+    builder = _LeafBuilder(spec)
+    exprs = [sp.sympify(spec.rhs[i]) for i in eq_indices]
+    symbols = sorted(
+        set().union(*[e.free_symbols for e in exprs]) if exprs else set(),
+        key=lambda s: s.name,
+    )
+    names, leaf_lines = {}, []
+    for n, s in enumerate(symbols):
+        ident = f"L{n}"
+        names[s.name] = ident
+        leaf_lines.append(
+            f"  const double {ident} = {builder.leaf(s.name)};  // {s.name}"
+        )
+    printer = _CudaPrinter(names)
+    out_lines = [
+        f"  out[{j}] = {printer.doprint(e)};" for j, e in enumerate(exprs)
+    ]
+    prim_lines = [
+        f"  const double {p} = {builder.prims[p]};" for p in builder.order
+    ]
+    body = "\n".join(prim_lines + leaf_lines + out_lines)
+    return (
+        f"__device__ __forceinline__ void {fn_name}(const PmlArgs& a, "
+        "const double* const* P, const PmlCell& c, double t, double* out) {\n"
+        "  (void)a; (void)P; (void)c; (void)t; (void)out;\n"
+        f"{body}\n}}\n"
+    )
+
+
+def _int_list(values) -> str:
+    values = list(values) or [0]
+    return "{" + ", ".join(str(int(v)) for v in values) + "}"
+
+
+def generate_source(spec: ProblemSpec) -> str:
+    nd = len(spec.shape)
+    if nd > 3:
+        raise NotImplementedError(
+            "the B200 FDM kernels support at most 3 spatial dimensions"
+        )
+    if any(n < 3 for n in spec.shape):
+        # numerical_differentiator.py:1021-1024
+        raise ValueError("y must contain at least 3 points along every x-axis")
+    n = list(spec.shape) + [1] * (3 - nd)
+    h = list(spec.d_x) + [1.0] * (3 - nd)
+    kinds = [KIND_CODES[k] for k in spec.kinds]
+    dt_idx = [i for i, k in enumerate(kinds) if k == 0]
+    alg_idx = [i for i, k in enumerate(kinds) if k == 1]
+    lap_idx = [i for i, k in enumerate(kinds) if k == 2]
+    block = spec.block or default_block(spec.shape)
+
+    lines = [
+        "// generated by pararealml_b200/operators/fdm/codegen.py",
+        f"#define PML_NDIM {nd}",
+        f"#define PML_C {spec.y_dim}",
+        f"#define PML_N0 {n[0]}",
+        f"#define PML_N1 {n[1]}",
+        f"#define PML_N2 {n[2]}",
+        f"#define PML_COORD {COORD_CODES[spec.coord]}",
+        f"#define PML_NEU_MASK {spec.neu_mask}",
+        f"#define PML_DIR_MASK {spec.dir_mask}",
+        f"#define PML_PASSTHROUGH {int(spec.passthrough)}",
+        f"#define PML_COHERENT_LOADS {int(spec.coherent_loads)}",
+        f"#define PML_NDT {len(dt_idx)}",
+        f"#define PML_NALG {len(alg_idx)}",
+        f"#define PML_NLAP {len(lap_idx)}",
+        f"#define PML_BX {block[0]}",
+        f"#define PML_BY {block[1]}",
+        f"#define PML_BZ {block[2]}",
+    ]
+    for a in range(3):
+        lines.append(f"#define PML_H{a} {c_double(h[a])}")
+        lines.append(f"#define PML_INV2H{a} {c_double(1.0 / (2.0 * h[a]))}")
+        lines.append(f"#define PML_INVHH{a} {c_double(1.0 / (h[a] * h[a]))}")
+    inv_diag = 1.0 / float((2.0 / np.square(np.array(spec.d_x))).sum()) if nd else 1.0
+    lines.append(f"#define PML_JAC_INV_DIAG {c_double(inv_diag)}")
+    lines.append(
+        f"static __device__ constexpr int PML_KIND[] = {_int_list(kinds)};"
+    )
+    lines.append(
+        f"static __device__ constexpr int PML_DT_IDX[] = {_int_list(dt_idx)};"
+    )
+    lines.append(
+        f"static __device__ constexpr int PML_ALG_IDX[] = {_int_list(alg_idx)};"
+    )
+    lines.append(
+        f"static __device__ constexpr int PML_LAP_IDX[] = {_int_list(lap_idx)};"
+    )
+    prelude = "\n".join(lines) + "\n"
+
+    rhs_code = _emit_function("pml_rhs_dt", spec, dt_idx) + _emit_function(
+        "pml_rhs_aux", spec, alg_idx + lap_idx
+    )
+    with open(TEMPLATE_PATH) as fh:
+        template = fh.read()
+    return prelude + template.replace("PML_GENERATED_RHS", rhs_code)
+
+
+def source_key(source: str) -> str:
+    return hashlib.sha256(source.encode()).hexdigest()[:24]

@@ -1,0 +1,246 @@
+"""``FDMOperator``: the drop-in finite difference solver on B200.
+
+Same constructor and ``solve(ivp, parallel_enabled=True) -> Solution`` as the
+reference (``pararealml/operators/fdm/fdm_operator.py:27-77``).  Underneath,
+the problem is lowered once (``lowering.py``), the SymPy right-hand side is
+emitted into the fixed CUDA template and compiled with NVRTC (``codegen.py``,
+``csrc/fdm_template.cuh``), and the whole time loop runs on the device through
+the C ABI (``pml_fdm_run``): the state, the stage buffers and the trajectory
+stay in HBM for all steps; the host only evaluates user Python callables
+(dynamic boundary conditions) and draws the Jacobi start values from NumPy's
+global generator like the reference does (numerical_differentiator.py:908-909).
+"""
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from pararealml_b200.operator import Operator, discretize_time_domain
+from pararealml_b200.operators.fdm import device as dv
+from pararealml_b200.operators.fdm.lowering import (
+    LoweredProblem,
+    apply_dirichlet_host,
+    dynamic_tables,
+    lower_problem,
+)
+from pararealml_b200.operators.fdm.numerical_differentiator import (
+    NumericalDifferentiator,
+)
+from pararealml_b200.operators.fdm.numerical_integrator import (
+    NumericalIntegrator,
+)
+from pararealml_b200.solution import Solution
+
+# device bytes one trajectory chunk may take before the solve is pipelined
+TRAJECTORY_CHUNK_BYTES = int(
+    os.environ.get("PML_TRAJ_CHUNK_BYTES", str(8 << 30))
+)
+# time steps per upload of dynamic boundary tables
+DYNAMIC_BC_CHUNK_STEPS = 256
+
+
+def lowered(cp) -> LoweredProblem:
+    """Lowering is cached on the constrained problem (Parareal solves the
+    same problem many times)."""
+    low = getattr(cp, "_pml_b200_lowered", None)
+    if low is None:
+        low = lower_problem(cp)
+        try:
+            cp._pml_b200_lowered = low
+        except AttributeError:
+            pass
+    return low
+
+
+class FDMOperator(Operator):
+    def __init__(
+        self,
+        integrator: NumericalIntegrator,
+        differentiator: NumericalDifferentiator,
+        d_t: float,
+    ):
+        super().__init__(d_t, True)
+        family = getattr(integrator, "kernel_family", "")
+        if family not in ("forward_euler", "explicit_midpoint", "rk4"):
+            raise NotImplementedError(
+                f"{type(integrator).__name__} has no fused stage kernels; the "
+                "B200 FDM path provides ForwardEulerMethod, "
+                "ExplicitMidpointMethod and RK4 and does not fall back to the "
+                "CPU"
+            )
+        self._integrator = integrator
+        self._differentiator = differentiator
+        self._family = family
+        #: Jacobi sweeps per time step of the most recent solve (systems with
+        #: LHS.Y_LAPLACIAN equations)
+        self.last_jacobi_sweeps = None
+        #: optional cap on Jacobi sweeps per step (0 = run to tolerance as the
+        #: reference does)
+        self.max_jacobi_sweeps = 0
+
+    # ------------------------------------------------------------------
+    # plan selection
+    # ------------------------------------------------------------------
+    def _plan_for(self, cp, low: LoweredProblem, y0: Optional[np.ndarray]):
+        for sym in set().union(*[e.free_symbols for e in low.rhs]):
+            if sym.name.startswith("y-vector-laplacian"):
+                # the reference's symbol mapper never stores this evaluator
+                # (symbol_mapper.py:215-218) and fails the same way
+                raise KeyError(sym)
+        passthrough = False
+        n_other = len(low.kinds) - len(low.kind_indices("D_Y_OVER_D_T"))
+        if n_other and low.all_static:
+            # the stage inputs of the non-dt components equal y itself when y
+            # already satisfies the (static) Dirichlet values
+            if low.dir_mask == 0:
+                passthrough = True
+            elif y0 is not None:
+                probe = apply_dirichlet_host(cp, np.array(y0, copy=True), None)
+                passthrough = bool(np.array_equal(probe, y0))
+        return dv.get_plan(low, passthrough=passthrough)
+
+    # ------------------------------------------------------------------
+    # device-resident integration (also used by the Parareal fast path)
+    # ------------------------------------------------------------------
+    def integrate_on_device(
+        self,
+        cp,
+        plan: "dv.DevicePlan",
+        y0_planes: torch.Tensor,
+        t: np.ndarray,
+        traj: torch.Tensor,
+    ):
+        """Advances ``y0_planes`` (component planes) through the steps
+        starting at ``t[:-1]`` and writes step j to ``traj[j]``."""
+        low = plan.low
+        n_steps = len(t) - 1
+        d_t = self._d_t
+        tol = getattr(self._differentiator, "_tol", 1e-3)
+        sweeps_log = []
+        if low.all_static or low.n_dims == 0:
+            plan.bind_tables(low)
+            jac = self._draw_jacobi_starts(plan, n_steps)
+            s = plan.run(
+                self._family, y0_planes, traj, t[:-1], d_t, 0, jac, tol,
+                self.max_jacobi_sweeps,
+            )
+            if s is not None:
+                sweeps_log.append(s)
+        else:
+            y_prev = y0_planes
+            for first in range(0, n_steps, DYNAMIC_BC_CHUNK_STEPS):
+                last = min(first + DYNAMIC_BC_CHUNK_STEPS, n_steps)
+                starts = t[first:last]
+                times = np.empty(3 * len(starts))
+                times[0::3] = starts
+                times[1::3] = starts + d_t / 2.0
+                times[2::3] = starts + d_t
+                dyn_neu, dyn_dir = dynamic_tables(cp, low, times)
+                plan.bind_tables(low, dyn_neu, dyn_dir)
+                jac = self._draw_jacobi_starts(plan, last - first)
+                s = plan.run(
+                    self._family, y_prev, traj[first:last], starts, d_t, 0,
+                    jac, tol, self.max_jacobi_sweeps,
+                )
+                if s is not None:
+                    sweeps_log.append(s)
+                y_prev = traj[last - 1]
+        self.last_jacobi_sweeps = (
+            np.concatenate(sweeps_log) if sweeps_log else None
+        )
+
+    @staticmethod
+    def _draw_jacobi_starts(plan, n_steps) -> Optional[torch.Tensor]:
+        if not plan.n_lap:
+            return None
+        low = plan.low
+        draws = np.empty((n_steps,) + low.shape + (plan.n_lap,))
+        for j in range(n_steps):
+            # one draw per time step from the global stream, like
+            # numerical_differentiator.py:908-909
+            draws[j] = np.random.random(low.shape + (plan.n_lap,))
+        return torch.from_numpy(draws).to(plan.device)
+
+    def prepare(self, ivp) -> Tuple:
+        """Host set-up shared by ``solve`` and the benchmarks: time grid,
+        initial state (with the dynamic constraints of t0 applied,
+        fdm_operator.py:56-63), lowering and plan."""
+        cp = ivp.constrained_problem
+        t = discretize_time_domain(ivp.t_interval, self._d_t)
+        y0 = ivp.initial_condition.discrete_y_0(True)
+        low = lowered(cp)
+        if low.n_dims and not low.all_static:
+            apply_dirichlet_host(cp, y0, float(t[0]))
+        plan = self._plan_for(cp, low, y0)
+        return cp, t, y0, low, plan
+
+    def solve_on_device(self, ivp, y0_planes: Optional[torch.Tensor] = None):
+        """Solves with the whole trajectory kept in HBM.  Returns
+        ``(t[1:], trajectory planes (n_steps, y_dim * n_cells))``."""
+        cp, t, y0, low, plan = self.prepare(ivp)
+        if y0_planes is None:
+            y0_planes = dv.upload_state(y0, low.n_cells, low.y_dim)
+        traj = torch.empty(
+            (len(t) - 1, low.y_dim * low.n_cells),
+            dtype=torch.float64, device=plan.device,
+        )
+        self.integrate_on_device(cp, plan, y0_planes, t, traj)
+        return t[1:], traj
+
+    # ------------------------------------------------------------------
+    # the drop-in entry point
+    # ------------------------------------------------------------------
+    def solve(self, ivp, parallel_enabled: bool = True) -> Solution:
+        cp, t, y0, low, plan = self.prepare(ivp)
+        n_steps = len(t) - 1
+        state = low.y_dim * low.n_cells
+        y_shape = cp.y_vertices_shape
+        host = torch.empty(
+            (n_steps, state), dtype=torch.float64, pin_memory=True
+        )
+        y_prev = dv.upload_state(y0, low.n_cells, low.y_dim)
+
+        chunk = max(1, min(n_steps, TRAJECTORY_CHUNK_BYTES // (state * 8)))
+        n_buf = 1 if chunk >= n_steps else 2
+        f64 = dict(dtype=torch.float64, device=plan.device)
+        bufs = [torch.empty((chunk, state), **f64) for _ in range(n_buf)]
+        need_stage = low.y_dim > 1 and low.n_cells > 1
+        stages = (
+            [torch.empty((chunk, state), **f64) for _ in range(n_buf)]
+            if need_stage else None
+        )
+        compute = torch.cuda.current_stream()
+        copier = torch.cuda.Stream() if n_buf > 1 else compute
+        drained = [None] * n_buf
+        sweeps = []
+        for k, first in enumerate(range(0, n_steps, chunk)):
+            last = min(first + chunk, n_steps)
+            b = k % n_buf
+            if drained[b] is not None:
+                compute.wait_event(drained[b])
+            traj = bufs[b][: last - first]
+            self.integrate_on_device(cp, plan, y_prev, t[first : last + 1], traj)
+            if self.last_jacobi_sweeps is not None:
+                sweeps.append(self.last_jacobi_sweeps)
+            y_prev = traj[last - first - 1]
+            filled = torch.cuda.Event()
+            filled.record(compute)
+            with torch.cuda.stream(copier):
+                copier.wait_event(filled)
+                src = traj
+                if need_stage:
+                    src = dv.soa_to_aos(
+                        traj, low.n_cells, low.y_dim, last - first,
+                        out=stages[b][: last - first],
+                    )
+                host[first:last].copy_(src, non_blocking=True)
+                drained[b] = torch.cuda.Event()
+                drained[b].record(copier)
+        copier.synchronize()
+        compute.synchronize()
+        self.last_jacobi_sweeps = np.concatenate(sweeps) if sweeps else None
+        y = host.numpy().reshape((n_steps,) + tuple(y_shape))
+        return Solution(
+            ivp, t[1:], y, vertex_oriented=True, d_t=self._d_t, copy=False
+        )
