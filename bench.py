@@ -1,0 +1,482 @@
+"""Benchmark of the B200 FDM + Parareal hot path (driver contract).
+
+N = 1   : fp64 RK4 ``FDMOperator`` time steps of the 3-D Burgers equation on a
+          512^3 mesh (BASELINE.json configs[4] grid, the largest configuration
+          that fits one GPU); a "step" is one RK4 time step (4 fused stage
+          kernels).  ``value`` is timed with the state resident in HBM,
+          ``e2e`` goes through ``FDMOperator.solve`` with host buffers.
+N > 1   : ``PararealOperator`` (fine RK4, coarse ForwardEuler) on the same
+          problem with one time slice per GPU (weak scaling: fixed fine steps
+          per slice); a "step" is one Parareal solve and ``value`` counts the
+          cell-steps of the fine-resolution trajectory it produces.
+
+``--impl reference`` times the oracle port of the reference's NumPy path
+(``oracle/``; the reference itself is pure Python and cannot travel to the GPU
+box) on a bounded sample of the same workload on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fp64 FDM cell-steps/s (3-D Burgers 512^3, RK4)"
+UNIT = "Gcell-steps/s"
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--grid", type=int, default=int(os.environ.get("PML_BENCH_GRID", "512")))
+    p.add_argument("--equation", default="burgers")
+    p.add_argument("--e2e-steps", type=int, default=4)
+    p.add_argument("--slice-steps", type=int, default=4,
+                   help="fine steps per Parareal time slice")
+    p.add_argument("--coarse-ratio", type=int, default=2,
+                   help="coarse step = ratio * fine step")
+    p.add_argument("--parareal-tol", type=float, default=1e-7)
+    p.add_argument("--cpu-grid", type=int, default=96)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    return p.parse_args()
+
+
+# ---------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------
+def gaussian_y0(n, y_dim=3):
+    """Separable Gaussian bumps (mean 0.5, variance 0.05 per axis, SURVEY.md
+    section 8d K5) evaluated directly on the mesh; equals the product-form of
+    GaussianInitialCondition for a diagonal covariance."""
+    x = np.linspace(0.0, 1.0, n)
+    g = np.exp(-0.5 * (x - 0.5) ** 2 / 0.05) / np.sqrt(2.0 * np.pi * 0.05)
+    field = g[:, None, None] * g[None, :, None] * g[None, None, :]
+    scales = [0.3, -0.2, 0.1][:y_dim]
+    y0 = np.empty((n, n, n, y_dim))
+    for c, s in enumerate(scales):
+        y0[..., c] = s * field
+    return y0
+
+
+def burgers_problem(ns, n, n_steps, d_t=None):
+    """K5: BurgersEquation(3, 100) on [0,1]^3 with n^3 vertices, zero-flux
+    boundaries.  The time step keeps the explicit scheme stable
+    (d_t <= d_x^2 Re / 6)."""
+    eq = ns.BurgersEquation(3, 100.0)
+    h = 1.0 / (n - 1)
+    mesh = ns.Mesh([(0.0, 1.0)] * 3, [h] * 3)
+    bc = ns.NeumannBoundaryCondition(
+        lambda x, t: np.zeros((len(x), 3)), is_static=True
+    )
+    cp = ns.ConstrainedProblem(eq, mesh, [(bc, bc)] * 3)
+    if d_t is None:
+        d_t = 0.1 * h * h * 100.0 / 6.0
+    ic = ns.DiscreteInitialCondition(cp, gaussian_y0(n), True)
+    ivp = ns.InitialValueProblem(cp, (0.0, n_steps * d_t), ic)
+    return ivp, d_t
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = (
+        "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+        "clocks_event_reasons.hw_thermal_slowdown,"
+        "clocks_event_reasons.sw_thermal_slowdown,"
+        "clocks_event_reasons.sw_power_cap"
+    )
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [s.strip() for s in line.split(",")]
+            if len(parts) >= 6:
+                self.rows.append(parts)
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for name, v in zip(self.NAMES, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {
+            "sm_mhz": float(np.median(sm)),
+            "sm_max_mhz": float(max(mx)),
+            "reasons": sorted(reasons),
+            "samples": len(sm),
+        }
+
+
+# ---------------------------------------------------------------------------
+# CPU baseline (oracle port of the reference's NumPy path)
+# ---------------------------------------------------------------------------
+def cpu_baseline(n, n_steps):
+    import oracle
+    import pararealml_b200 as ns
+
+    ivp, d_t = burgers_problem(ns, n, n_steps)
+    t0 = time.perf_counter()
+    oracle.fdm_solve(ivp, "rk4", d_t)
+    dt = time.perf_counter() - t0
+    return n**3 * n_steps / dt / 1e9, dt
+
+
+def peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic():
+    """dram bytes per step from the committed ncu capture, if any."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh)
+    return {}
+
+
+# ---------------------------------------------------------------------------
+# reference arm
+# ---------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    import pararealml_b200 as ns
+
+    n = args.cpu_grid
+    ivp, d_t = burgers_problem(ns, n, 1)
+    from oracle.fdm import fdm_solve
+
+    cp = ivp.constrained_problem
+    y = ivp.initial_condition.discrete_y_0(True)
+
+    def one_step(y_in):
+        sub = ns.InitialValueProblem(
+            cp, (0.0, d_t), ns.DiscreteInitialCondition(cp, y_in, True)
+        )
+        return fdm_solve(sub, "rk4", d_t)[1][-1]
+
+    for _ in range(args.warmup):
+        y = one_step(y)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        y = one_step(y)
+    dt = time.perf_counter() - t0
+    value = n**3 * args.steps / dt / 1e9
+    sample = (
+        f"oracle port of the reference NumPy FDMOperator (RK4, "
+        f"ThreePointCentralDifferenceMethod), 3-D Burgers on {n}^3 "
+        f"(bounded sample of the 512^3 workload), {args.steps} steps, "
+        "single process (NumPy stencils are single-threaded)"
+    )
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"3-D Burgers RK4 FDM, {n}^3 sample of the 512^3 workload"},
+        "cpu_baseline": {
+            "value": value, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": sample,
+        },
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import pararealml_b200 as ns
+    from pararealml_b200.operators.fdm import (
+        RK4,
+        FDMOperator,
+        ForwardEulerMethod,
+        ThreePointCentralDifferenceMethod,
+    )
+    from pararealml_b200.operators.fdm import device as dv
+    from pararealml_b200.operators.parareal import PararealOperator
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n = args.grid
+    cells = n**3
+    y_dim = 3
+    peak, peak_src = peak_hbm()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if world == 1:
+        # ---- device-resident RK4 steps --------------------------------
+        total = args.warmup + args.steps
+        ivp, d_t = burgers_problem(ns, n, total)
+        op = FDMOperator(RK4(), ThreePointCentralDifferenceMethod(), d_t)
+        cp, t, y0, low, plan = op.prepare(ivp)
+        y_dev = dv.upload_state(y0, low.n_cells, low.y_dim)
+        traj = torch.empty((total, y_dim * cells), dtype=torch.float64, device="cuda")
+        op.integrate_on_device(cp, plan, y_dev, t[: args.warmup + 1], traj[: args.warmup])
+        barrier()
+        launches0 = dv.total_launches()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as clocks:
+            start.record()
+            op.integrate_on_device(
+                cp, plan, traj[args.warmup - 1], t[args.warmup:], traj[args.warmup:]
+            )
+            stop.record()
+            barrier()
+        ms = start.elapsed_time(stop)
+        launches = dv.total_launches() - launches0
+        finite = bool(torch.isfinite(traj[-1]).all().item())
+        value = cells * args.steps / (ms * 1e-3) / 1e9
+        alg_bytes_step = 128 * y_dim * cells
+        achieved = alg_bytes_step * args.steps / (ms * 1e-3) / 1e9
+        del traj, y_dev
+        torch.cuda.empty_cache()
+
+        # ---- end to end through FDMOperator.solve (host buffers) -----------
+        e2e = None
+        if not args.no_e2e:
+            ivp_e, d_t_e = burgers_problem(ns, n, args.e2e_steps)
+            op_e = FDMOperator(RK4(), ThreePointCentralDifferenceMethod(), d_t_e)
+            op_e.solve(ivp_e)  # warm-up (pinned buffers, plan)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            sol = op_e.solve(ivp_e)
+            torch.cuda.synchronize()
+            dt_e = time.perf_counter() - t0
+            state_bytes = cells * y_dim * 8
+            e2e = {
+                "value": cells * args.e2e_steps / dt_e / 1e9,
+                "unit": UNIT,
+                "h2d_bytes_per_step": state_bytes // args.e2e_steps,
+                "d2h_bytes_per_step": state_bytes,
+                "steps": args.e2e_steps,
+                "note": "FDMOperator.solve(ivp): H2D of y0, device time loop, "
+                        "D2H of every step of the trajectory into the returned "
+                        "Solution",
+            }
+            del sol
+        cpu = None
+        if not args.no_cpu_baseline:
+            v, secs = cpu_baseline(args.cpu_grid, 2)
+            cpu = {
+                "value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": f"oracle port of the reference NumPy RK4 FDM path, "
+                          f"3-D Burgers {args.cpu_grid}^3, 2 steps, {secs:.1f} s, "
+                          f"single process ({os.cpu_count()} host cores present)",
+            }
+        traffic = load_traffic().get("rk4_step_dram_bytes_512")
+        line = {
+            "metric": METRIC,
+            "value": value,
+            "unit": UNIT,
+            "n_gpus": 1,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": ms / args.steps,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f64",
+            "data": "synthetic",
+            "config": {
+                "workload": f"FDMOperator(RK4, ThreePointCentralDifferenceMethod) "
+                            f"on BurgersEquation(3, Re=100), {n}^3 mesh, "
+                            "zero-flux boundaries, Gaussian initial condition",
+                "grid": [n, n, n], "y_dim": y_dim, "d_t": d_t,
+                "cache": "state (3.2 GB at 512^3) is larger than L2",
+                "finite": finite,
+            },
+            "clocks": clocks.summary(),
+            "roofline": {
+                "bound": "hbm",
+                "achieved": achieved,
+                "peak": peak,
+                "unit": "GB/s",
+                "frac": achieved / peak,
+                "traffic": traffic,
+                "peak_source": peak_src,
+                "algorithmic_bytes_per_cell_step": 128 * y_dim,
+                "launches_per_step": 4,
+            },
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": launches,
+        }
+        print(json.dumps(line), flush=True)
+        return
+
+    # ---- N > 1: Parareal, one time slice per GPU ----------------------------
+    s_steps = args.slice_steps
+    total_steps = world * s_steps
+    ivp, d_t = burgers_problem(ns, n, total_steps)
+    f = FDMOperator(RK4(), ThreePointCentralDifferenceMethod(), d_t)
+    g = FDMOperator(
+        ForwardEulerMethod(), ThreePointCentralDifferenceMethod(),
+        d_t * args.coarse_ratio,
+    )
+    p = PararealOperator(f, g, args.parareal_tol, gather_trajectory=False)
+    for _ in range(args.warmup):
+        p.solve(ivp)
+    barrier()
+    launches0 = dv.total_launches()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        start.record()
+        for _ in range(args.steps):
+            p.solve(ivp)
+        stop.record()
+        barrier()
+    ms = torch.tensor([start.elapsed_time(stop)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    launches = dv.total_launches() - launches0
+    iterations = p.last_iterations
+
+    e2e = None
+    if not args.no_e2e:
+        pe = PararealOperator(f, g, args.parareal_tol)  # gathers to every rank
+        barrier()
+        t0 = time.perf_counter()
+        sol = pe.solve(ivp)
+        barrier()
+        dt_e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(dt_e, op=dist.ReduceOp.MAX)
+        state_bytes = cells * y_dim * 8
+        e2e = {
+            "value": cells * total_steps / float(dt_e.item()) / 1e9,
+            "unit": UNIT,
+            "h2d_bytes_per_step": state_bytes,
+            "d2h_bytes_per_step": state_bytes * total_steps,
+            "note": "PararealOperator.solve(ivp) incl. H2D of y0 and the "
+                    "all-gather + D2H of the full trajectory on every rank",
+        }
+        del sol
+    if rank == 0:
+        value = cells * total_steps * args.steps / (ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC,
+            "value": value,
+            "unit": UNIT,
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": ms / args.steps,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f64",
+            "data": "synthetic",
+            "config": {
+                "workload": f"PararealOperator(f=FDM RK4 d_t, g=FDM ForwardEuler "
+                            f"{args.coarse_ratio} d_t) on BurgersEquation(3, "
+                            f"Re=100), {n}^3 mesh, {world} time slices x "
+                            f"{s_steps} fine steps, tol {args.parareal_tol}",
+                "grid": [n, n, n], "y_dim": y_dim, "d_t": d_t,
+                "parareal_iterations": iterations,
+                "cache": "state (3.2 GB at 512^3) is larger than L2",
+            },
+            "clocks": clocks.summary(),
+            "roofline": {
+                "bound": "hbm",
+                "achieved": 128 * y_dim * value,
+                "peak": peak * world,
+                "unit": "GB/s",
+                "frac": 128 * y_dim * value / (peak * world),
+                "traffic": None,
+                "peak_source": peak_src,
+                "note": "useful fine-trajectory bytes only; Parareal repeats "
+                        "fine solves once per iteration",
+            },
+            "cpu_baseline": None,
+            "e2e": e2e,
+            "gpu_launches": launches,
+        }
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

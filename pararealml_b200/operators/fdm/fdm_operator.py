@@ -53,6 +53,26 @@ def lowered(cp) -> LoweredProblem:
     return low
 
 
+def plan_overrides(cp, low: LoweredProblem, y0: Optional[np.ndarray]) -> dict:
+    """Code generation switches of the stage kernels for this problem."""
+    for sym in set().union(*[e.free_symbols for e in low.rhs]):
+        if sym.name.startswith("y-vector-laplacian"):
+            # the reference's symbol mapper never stores this evaluator
+            # (symbol_mapper.py:215-218) and fails the same way
+            raise KeyError(sym)
+    passthrough = False
+    n_other = len(low.kinds) - len(low.kind_indices("D_Y_OVER_D_T"))
+    if n_other and low.all_static and low.n_dims:
+        # the stage inputs of the non-dt components equal y itself when y
+        # already satisfies the (static) Dirichlet values
+        if low.dir_mask == 0:
+            passthrough = True
+        elif y0 is not None:
+            probe = apply_dirichlet_host(cp, np.array(y0, copy=True), None)
+            passthrough = bool(np.array_equal(probe, y0))
+    return {"passthrough": passthrough}
+
+
 class FDMOperator(Operator):
     def __init__(
         self,
@@ -83,22 +103,7 @@ class FDMOperator(Operator):
     # plan selection
     # ------------------------------------------------------------------
     def _plan_for(self, cp, low: LoweredProblem, y0: Optional[np.ndarray]):
-        for sym in set().union(*[e.free_symbols for e in low.rhs]):
-            if sym.name.startswith("y-vector-laplacian"):
-                # the reference's symbol mapper never stores this evaluator
-                # (symbol_mapper.py:215-218) and fails the same way
-                raise KeyError(sym)
-        passthrough = False
-        n_other = len(low.kinds) - len(low.kind_indices("D_Y_OVER_D_T"))
-        if n_other and low.all_static:
-            # the stage inputs of the non-dt components equal y itself when y
-            # already satisfies the (static) Dirichlet values
-            if low.dir_mask == 0:
-                passthrough = True
-            elif y0 is not None:
-                probe = apply_dirichlet_host(cp, np.array(y0, copy=True), None)
-                passthrough = bool(np.array_equal(probe, y0))
-        return dv.get_plan(low, passthrough=passthrough)
+        return dv.get_plan(low, **plan_overrides(cp, low, y0))
 
     # ------------------------------------------------------------------
     # device-resident integration (also used by the Parareal fast path)

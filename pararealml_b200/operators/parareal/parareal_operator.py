@@ -1,0 +1,406 @@
+"""``PararealOperator``: time-parallel driver, one rank per GPU.
+
+Same constructor and ``solve`` as the reference
+(``pararealml/operators/parareal/parareal_operator.py:13-197``).  The
+reference runs one MPI rank per time slice, recomputes the serial coarse sweep
+redundantly on every rank and moves data with two ``MPI_Allgather`` calls
+(:165, :193).  Here a rank is a process bound to one GPU
+(``torch.distributed``; NCCL over NVLink on GPUs, gloo in CPU tests) and the
+sweep is a pipeline:
+
+* every rank keeps only its own slice state: start ``U_r``, end estimate
+  ``U_{r+1}``, coarse end ``G_r``, correction ``F_r - G_r`` and its fine
+  trajectory;
+* in iteration ``i`` rank ``i`` forms ``U_{i+1} = G_i + corr_i`` and sends it
+  to rank ``i + 1``; each later rank receives its new start, propagates it
+  with the coarse operator, adds its correction and passes the result on
+  (point-to-point send/recv of one state per hop);
+* convergence is the reference's test (:53-100): per component the maximum
+  over slices of the RMS end point update, obtained with an all-reduce(MAX)
+  of ``y_dimension`` doubles;
+* the arithmetic ``G + (F - G)``, the single full-interval initial coarse
+  solve (:133-139), the frozen slices ``< i`` (:168), and the final rigid
+  shift of each slice trajectory (:192) are kept, so trajectories and
+  iteration counts match the reference.
+
+When both operators are ``FDMOperator`` and the boundary conditions are static
+all states stay on the device (component planes) and the updates run as CUDA
+kernels through the C ABI (``pml_parareal_*``); any other ``Operator`` pair
+goes through the generic path that exchanges host arrays.
+"""
+import ctypes
+import sys
+from typing import Callable, Optional, Sequence, Union
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from pararealml_b200 import _native
+from pararealml_b200.initial_condition import DiscreteInitialCondition
+from pararealml_b200.initial_value_problem import InitialValueProblem
+from pararealml_b200.operator import Operator, discretize_time_domain
+from pararealml_b200.solution import Solution
+
+TerminationCondition = Union[
+    float, Sequence[float], Callable[[np.ndarray, np.ndarray], bool]
+]
+
+
+class _World:
+    """The set of time-slice ranks: ``torch.distributed``'s default group, or
+    a single rank when no process group is initialised."""
+
+    def __init__(self):
+        self.active = dist.is_available() and dist.is_initialized()
+        self.size = dist.get_world_size() if self.active else 1
+        self.rank = dist.get_rank() if self.active else 0
+        backend = dist.get_backend() if self.active else "none"
+        self.on_gpu = backend == "nccl"
+
+    def comm_device(self) -> torch.device:
+        if self.on_gpu:
+            return torch.device("cuda", torch.cuda.current_device())
+        return torch.device("cpu")
+
+    # A gloo group (CPU tests, or several ranks sharing one GPU) moves device
+    # tensors through host staging; an NCCL group moves them GPU to GPU.
+    def _staged(self, t: torch.Tensor) -> bool:
+        return t.is_cuda and not self.on_gpu
+
+    def send(self, t: torch.Tensor, dst: int):
+        dist.send(t.cpu() if self._staged(t) else t, dst)
+
+    def recv(self, t: torch.Tensor, src: int):
+        if self._staged(t):
+            tmp = torch.empty(t.shape, dtype=t.dtype)
+            dist.recv(tmp, src)
+            t.copy_(tmp)
+        else:
+            dist.recv(t, src)
+
+    def all_reduce_max(self, t: torch.Tensor):
+        if not self.active:
+            return
+        if self._staged(t):
+            tmp = t.cpu()
+            dist.all_reduce(tmp, op=dist.ReduceOp.MAX)
+            t.copy_(tmp)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+
+    def all_gather(self, t: torch.Tensor) -> torch.Tensor:
+        """Every rank's ``t`` stacked along a new first axis."""
+        if not self.active:
+            return t.unsqueeze(0)
+        src = t.cpu() if self._staged(t) else t
+        out = torch.empty(
+            (self.size,) + tuple(t.shape), dtype=t.dtype, device=src.device
+        )
+        dist.all_gather_into_tensor(out.view(-1), src.contiguous().view(-1))
+        return out.to(t.device) if self._staged(t) else out
+
+
+def _tolerances(condition, y_dim: int) -> np.ndarray:
+    """reference :68-83"""
+    if isinstance(condition, Sequence):
+        if len(condition) != y_dim:
+            raise ValueError(
+                f"length of update tolerances ({len(condition)}) must match "
+                f"number of y dimensions ({y_dim})"
+            )
+        return np.array(condition)
+    return np.array([condition] * y_dim)
+
+
+class PararealOperator(Operator):
+    def __init__(
+        self,
+        f: Operator,
+        g: Operator,
+        termination_condition: TerminationCondition = None,
+        max_iterations: int = sys.maxsize,
+        gather_trajectory: bool = True,
+    ):
+        """``gather_trajectory`` (extension): if False the returned
+        ``Solution`` gathers the slice trajectories lazily on the first
+        access of its values (a collective: every rank must then read it)."""
+        super().__init__(f.d_t, f.vertex_oriented)
+        self._f = f
+        self._g = g
+        self._termination_condition = termination_condition
+        self._max_iterations = max_iterations
+        self._gather_trajectory = gather_trajectory
+        #: corrective iterations executed by the most recent solve
+        self.last_iterations = 0
+        #: device planes of this rank's fine slice after the last solve
+        #: (fast path) -- the sharded trajectory
+        self.last_slice_trajectory = None
+
+    # ------------------------------------------------------------------
+    def _should_terminate(
+        self, old_y_end_points: np.ndarray, new_y_end_points: np.ndarray
+    ) -> bool:
+        """Host form of the convergence test on full end point arrays
+        (reference :53-100); used for callable conditions and by tests."""
+        cond = self._termination_condition
+        if callable(cond):
+            return cond(old_y_end_points, new_y_end_points)
+        y_dim = old_y_end_points.shape[-1]
+        tol = _tolerances(cond, y_dim)
+        worst = np.zeros(y_dim)
+        for c in range(y_dim):
+            for new, old in zip(
+                new_y_end_points[..., c], old_y_end_points[..., c]
+            ):
+                worst[c] = np.maximum(
+                    worst[c], np.sqrt(np.square(new - old).mean())
+                )
+        return all(worst < tol)
+
+    @staticmethod
+    def _check_divisibility(delta_t: float, op: Operator, name: str):
+        if not np.isclose(delta_t, op.d_t * round(delta_t / op.d_t)):
+            raise ValueError(
+                f"{name} operator time step size ({op.d_t}) must be a "
+                f"divisor of sub-IVP time slice length ({delta_t})"
+            )
+
+    def _device_path_available(self, cp, world) -> bool:
+        from pararealml_b200.operators.fdm.fdm_operator import (
+            FDMOperator,
+            lowered,
+        )
+
+        if not (
+            isinstance(self._f, FDMOperator)
+            and isinstance(self._g, FDMOperator)
+            and torch.cuda.is_available()
+            and not callable(self._termination_condition)
+        ):
+            return False
+        low = lowered(cp)
+        return bool(low.all_static or low.n_dims == 0)
+
+    # ------------------------------------------------------------------
+    def solve(self, ivp, parallel_enabled: bool = True) -> Solution:
+        if not parallel_enabled:
+            return self._f.solve(ivp)
+        world = _World()
+        t_interval = ivp.t_interval
+        delta_t = (t_interval[1] - t_interval[0]) / world.size
+        self._check_divisibility(delta_t, self._f, "fine")
+        self._check_divisibility(delta_t, self._g, "coarse")
+        cp = ivp.constrained_problem
+        if self._device_path_available(cp, world):
+            return self._solve_on_device(ivp, world)
+        return self._solve_generic(ivp, world)
+
+    # ------------------------------------------------------------------
+    # generic path: arbitrary operators, host arrays
+    # ------------------------------------------------------------------
+    def _solve_generic(self, ivp, world: _World) -> Solution:
+        f, g = self._f, self._g
+        vo = self._vertex_oriented
+        cp = ivp.constrained_problem
+        t0, t1 = ivp.t_interval
+        size, rank = world.size, world.rank
+        y_shape = cp.y_shape(vo)
+        y_dim = y_shape[-1]
+        borders = np.linspace(t0, t1, size + 1)
+        dev = world.comm_device()
+
+        def sub_ivp(r, y_start):
+            return InitialValueProblem(
+                cp,
+                (borders[r], borders[r + 1]),
+                DiscreteInitialCondition(cp, y_start, vo),
+            )
+
+        def to_comm(a: np.ndarray) -> torch.Tensor:
+            return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+        coarse = g.solve(ivp).discrete_y(vo)
+        ends = np.rint((borders[1:] - t0) / g.d_t).astype(int) - 1
+        g_end = np.array(coarse[ends[rank]], copy=True)
+        u_start = (
+            ivp.initial_condition.discrete_y_0(vo)
+            if rank == 0
+            else np.array(coarse[ends[rank - 1]], copy=True)
+        )
+        u_end = np.array(g_end, copy=True)
+        del coarse
+
+        fine = None
+        corr = None
+        self.last_iterations = 0
+        for i in range(min(size, self._max_iterations)):
+            self.last_iterations += 1
+            if fine is None or rank >= i:
+                fine = f.solve(sub_ivp(rank, u_start), False).discrete_y(vo)
+            corr = fine[-1] - g_end
+            old_end = u_end
+            if rank >= i:
+                if rank > i:
+                    buf = torch.empty(y_shape, dtype=torch.float64, device=dev)
+                    world.recv(buf, rank - 1)
+                    u_start = buf.cpu().numpy()
+                    g_end = g.solve(sub_ivp(rank, u_start)).discrete_y(vo)[-1]
+                u_end = g_end + corr
+                if rank + 1 < size:
+                    world.send(to_comm(u_end), rank + 1)
+            if callable(self._termination_condition):
+                olds = world.all_gather(to_comm(old_end)).cpu().numpy()
+                news = world.all_gather(to_comm(u_end)).cpu().numpy()
+                done = bool(self._termination_condition(olds, news))
+            else:
+                tol = _tolerances(self._termination_condition, y_dim)
+                rms = np.array(
+                    [
+                        np.sqrt(np.square(u_end[..., c] - old_end[..., c]).mean())
+                        for c in range(y_dim)
+                    ]
+                )
+                worst = to_comm(rms)
+                world.all_reduce_max(worst)
+                done = bool(np.all(worst.cpu().numpy() < tol))
+            if done:
+                break
+
+        fine = fine + (u_end - fine[-1])
+        t = discretize_time_domain(ivp.t_interval, f.d_t)[1:]
+
+        def gather() -> np.ndarray:
+            if size == 1:
+                return fine
+            parts = world.all_gather(to_comm(fine)).cpu().numpy()
+            return parts.reshape((len(t),) + tuple(y_shape))
+
+        y = gather() if self._gather_trajectory else gather
+        return Solution(ivp, t, y, vertex_oriented=vo, d_t=f.d_t, copy=False)
+
+    # ------------------------------------------------------------------
+    # device path: both operators are FDMOperator, static boundary conditions
+    # ------------------------------------------------------------------
+    def _solve_on_device(self, ivp, world: _World) -> Solution:
+        from pararealml_b200.operators.fdm import device as dv
+        from pararealml_b200.operators.fdm.fdm_operator import lowered
+
+        f, g = self._f, self._g
+        cp = ivp.constrained_problem
+        t0, t1 = ivp.t_interval
+        size, rank = world.size, world.rank
+        borders = np.linspace(t0, t1, size + 1)
+        low = lowered(cp)
+        n_cells, y_dim = low.n_cells, low.y_dim
+        state = n_cells * y_dim
+        y_shape = cp.y_shape(True)
+        lib = _native.lib()
+        device = dv.require_cuda()
+        f64 = dict(dtype=torch.float64, device=device)
+
+        # initial state with the static Dirichlet values re-applied, as the
+        # DiscreteInitialCondition of every sub-IVP does (reference :159-161)
+        y0 = DiscreteInitialCondition(
+            cp, ivp.initial_condition.discrete_y_0(True), True
+        ).discrete_y_0(True)
+        f_plan = f._plan_for(cp, low, y0)
+        g_plan = g._plan_for(cp, low, y0)
+
+        # one full-interval coarse solve on every rank (reference :133-139),
+        # run slice by slice so that only one slice of it is resident
+        t_g = discretize_time_domain(ivp.t_interval, g.d_t)
+        ends = np.rint((borders[1:] - t0) / g.d_t).astype(int) - 1
+        u_start = dv.upload_state(y0, n_cells, y_dim)
+        g_end = torch.empty(state, **f64)
+        prev = u_start
+        first = 0
+        seg = None
+        for r in range(rank + 1):
+            last = int(ends[r]) + 1
+            if seg is None or seg.shape[0] != last - first:
+                seg = torch.empty((last - first, state), **f64)
+            g.integrate_on_device(cp, g_plan, prev, t_g[first : last + 1], seg)
+            if r == rank:
+                g_end.copy_(seg[-1])
+            else:
+                prev = seg[-1].clone()
+                if r == rank - 1:
+                    u_start = prev
+            first = last
+        del seg
+        u_end = g_end.clone()
+
+        # this rank's fine and coarse time grids (slice-local, like the
+        # sub-IVPs of the reference)
+        t_f = discretize_time_domain((borders[rank], borders[rank + 1]), f.d_t)
+        t_gs = discretize_time_domain((borders[rank], borders[rank + 1]), g.d_t)
+        fine = torch.empty((len(t_f) - 1, state), **f64)
+        g_slice = torch.empty((len(t_gs) - 1, state), **f64)
+        corr = torch.empty(state, **f64)
+        new_end = torch.empty(state, **f64)
+        sumsq = torch.zeros(y_dim, **f64)
+        scratch = torch.empty(y_dim * 1024, **f64)
+        tol = _tolerances(self._termination_condition, y_dim)
+        stream = dv.stream_ptr
+
+        have_fine = False
+        self.last_iterations = 0
+        for i in range(min(size, self._max_iterations)):
+            self.last_iterations += 1
+            if not have_fine or rank >= i:
+                f.integrate_on_device(cp, f_plan, u_start, t_f, fine)
+                have_fine = True
+            _native.check(
+                lib.pml_parareal_correction(
+                    fine[-1].data_ptr(), g_end.data_ptr(), corr.data_ptr(),
+                    state, stream(),
+                )
+            )
+            sumsq.zero_()
+            if rank >= i:
+                if rank > i:
+                    world.recv(u_start, rank - 1)
+                    g.integrate_on_device(cp, g_plan, u_start, t_gs, g_slice)
+                    g_end.copy_(g_slice[-1])
+                _native.check(
+                    lib.pml_parareal_update(
+                        g_end.data_ptr(), corr.data_ptr(), u_end.data_ptr(),
+                        new_end.data_ptr(), sumsq.data_ptr(),
+                        scratch.data_ptr(), n_cells, y_dim, stream(),
+                    )
+                )
+                u_end, new_end = new_end, u_end
+                if rank + 1 < size:
+                    world.send(u_end, rank + 1)
+            worst = torch.sqrt(sumsq / n_cells)
+            world.all_reduce_max(worst)
+            if bool(np.all(worst.cpu().numpy() < tol)):
+                break
+
+        shift_tmp = torch.empty(state, **f64)
+        _native.check(
+            lib.pml_parareal_shift(
+                fine.data_ptr(), fine.shape[0], fine.stride(0),
+                u_end.data_ptr(), shift_tmp.data_ptr(), state, stream(),
+            )
+        )
+        self.last_slice_trajectory = fine
+        t = discretize_time_domain(ivp.t_interval, f.d_t)[1:]
+        n_local = fine.shape[0]
+
+        def gather() -> np.ndarray:
+            aos = dv.soa_to_aos(fine, n_cells, y_dim, n_local)
+            if size == 1:
+                host = torch.empty(aos.shape, dtype=torch.float64, pin_memory=True)
+                host.copy_(aos)
+                torch.cuda.current_stream().synchronize()
+                return host.numpy().reshape((len(t),) + tuple(y_shape))
+            full = world.all_gather(aos)
+            host = torch.empty(full.shape, dtype=torch.float64, pin_memory=True)
+            host.copy_(full)
+            torch.cuda.current_stream().synchronize()
+            return host.numpy().reshape((len(t),) + tuple(y_shape))
+
+        y = gather() if self._gather_trajectory else gather
+        return Solution(ivp, t, y, vertex_oriented=True, d_t=f.d_t, copy=False)

@@ -1,0 +1,122 @@
+"""Parity of the CUDA FDM path (through FDMOperator.solve -> C ABI) with the
+reference's trajectories (golden fixtures) and with the oracle on the same
+inputs.  fp64 tolerances: <= 1e-12 relative per step, <= 1e-9 on the final
+state (BASELINE.json north_star); chaotic ODE cases are compared per step over
+their short horizon with 1e-10."""
+import numpy as np
+import pytest
+
+import oracle
+import pararealml_b200 as ns
+from common import load_golden, per_step_rel_err, rel_err
+from golden import cases
+from pararealml_b200.operators.fdm import (
+    RK4,
+    ExplicitMidpointMethod,
+    FDMOperator,
+    ForwardEulerMethod,
+    ThreePointCentralDifferenceMethod,
+)
+
+pytestmark = pytest.mark.gpu
+
+INTEGRATORS = {
+    "rk4": RK4,
+    "explicit_midpoint": ExplicitMidpointMethod,
+    "forward_euler": ForwardEulerMethod,
+}
+
+
+def make_operator(case):
+    return FDMOperator(
+        INTEGRATORS[case.integrator](),
+        ThreePointCentralDifferenceMethod(case.tol),
+        case.d_t,
+    )
+
+
+def step_tolerance(case):
+    if "jacobi" in case.tags:
+        return case.rtol_traj
+    return 1e-10 if case.name.startswith("lorenz") else 1e-12
+
+
+@pytest.mark.parametrize("case", cases.FDM_CASES, ids=lambda c: c.name)
+def test_cuda_fdm_matches_reference_golden(case):
+    g = load_golden(case.name)
+    ivp = case.build(ns)
+    if case.seed is not None:
+        np.random.seed(case.seed)
+    sol = make_operator(case).solve(ivp)
+    y = sol.discrete_y()
+    assert y.shape == (int(g["n_steps"]),) + g["y"].shape[1:]
+    assert np.array_equal(sol.t_coordinates[g["steps"]], g["t"])
+    assert per_step_rel_err(y[g["steps"]], g["y"]) <= step_tolerance(case)
+    assert rel_err(y[-1], g["y"][-1]) <= 1e-9
+
+
+@pytest.mark.parametrize(
+    "case",
+    [c for c in cases.FDM_CASES if "jacobi" not in c.tags],
+    ids=lambda c: c.name,
+)
+def test_cuda_fdm_matches_oracle_every_step(case):
+    ivp = case.build(ns)
+    y = make_operator(case).solve(ivp).discrete_y()
+    _, y_oracle = oracle.fdm_solve(ivp, case.integrator, case.d_t, case.tol)
+    assert per_step_rel_err(y, y_oracle) <= step_tolerance(case)
+
+
+def test_navier_stokes_jacobi_sweep_counts_match_oracle():
+    case = cases.FDM_BY_NAME["navier_stokes_2d_rk4"]
+    ivp = case.build(ns)
+    np.random.seed(3)
+    op = make_operator(case)
+    y = op.solve(ivp).discrete_y()
+    stats = {}
+    np.random.seed(3)
+    _, y_oracle = oracle.fdm_solve(ivp, "rk4", case.d_t, case.tol, stats=stats)
+    assert list(op.last_jacobi_sweeps) == stats["jacobi_sweeps"]
+    assert per_step_rel_err(y, y_oracle) <= 1e-9
+
+
+def test_chunked_pipelined_solve_equals_single_chunk(monkeypatch):
+    """The trajectory pipeline (device chunk ring + copy stream) must not
+    change results."""
+    from pararealml_b200.operators.fdm import fdm_operator
+
+    case = cases.FDM_BY_NAME["wave_2d_dynamic_rk4"]
+    ivp = case.build(ns)
+    whole = make_operator(case).solve(ivp).discrete_y()
+    state_bytes = whole[0].size * 8
+    monkeypatch.setattr(fdm_operator, "TRAJECTORY_CHUNK_BYTES", 7 * state_bytes)
+    chunked = make_operator(case).solve(ivp).discrete_y()
+    assert np.array_equal(whole, chunked)
+
+
+def test_reference_problem_objects_are_accepted():
+    """Drop-in: an IVP built from the REFERENCE's own classes (when present)
+    is solved by the B200 operator."""
+    import refshim
+
+    if not refshim.available():
+        pytest.skip("reference not present on this machine")
+    ref = refshim.install()
+    case = cases.FDM_BY_NAME["convection_diffusion_2d_mixed_rk4"]
+    g = load_golden(case.name)
+    y = make_operator(case).solve(case.build(ref)).discrete_y()
+    assert per_step_rel_err(y[g["steps"]], g["y"]) <= 1e-12
+
+
+def test_solve_on_device_keeps_the_trajectory_in_hbm():
+    import torch
+
+    case = cases.FDM_BY_NAME["burgers_3d_cartesian_rk4"]
+    g = load_golden(case.name)
+    ivp = case.build(ns)
+    t, traj = make_operator(case).solve_on_device(ivp)
+    assert traj.is_cuda and traj.dtype == torch.float64
+    n = 12**3
+    planes = traj.cpu().numpy().reshape(len(t), 3, n)
+    y = np.moveaxis(planes, 1, 2).reshape((len(t), 12, 12, 12, 3))
+    assert per_step_rel_err(y[g["steps"]], g["y"]) <= 1e-12
