@@ -113,13 +113,16 @@ __device__ __forceinline__ double pml_neu(const PmlArgs& a, int comp, int i0,
 
 // first derivative along A at an arbitrary cell: zero ghost cells, boundary
 // planes overwritten by the Neumann value where one exists
-template <int A>
+// INT = true: the cell is known to be interior (no axis coordinate on a domain
+// face), all boundary handling compiles away and the loads are unconditional
+template <int A, bool INT>
 __device__ __forceinline__ double pml_d1_at(const PmlArgs& a,
                                             const double* __restrict__ p,
                                             int comp, int i0, int i1, int i2) {
   typedef PmlAx<A> X;
-  const int ia = pml_ia<A>(i0, i1, i2);
   const i64 idx = pml_lin(i0, i1, i2);
+  if (INT) return (PML_LD(p + idx + X::S) - PML_LD(p + idx - X::S)) * X::INV2H;
+  const int ia = pml_ia<A>(i0, i1, i2);
   const double lo = ia > 0 ? PML_LD(p + idx - X::S) : 0.0;
   const double hi = ia < X::N - 1 ? PML_LD(p + idx + X::S) : 0.0;
   double d = (hi - lo) * X::INV2H;
@@ -136,14 +139,19 @@ __device__ __forceinline__ double pml_d1_at(const PmlArgs& a,
 
 // neighbour sum / difference helpers with the second-difference ghost rule:
 // ghost = inner neighbour -/+ 2 h g where a Neumann value g exists, else 0
-template <int A>
+template <int A, bool INT>
 __device__ __forceinline__ void pml_nb2(const PmlArgs& a,
                                         const double* __restrict__ p, int comp,
                                         int i0, int i1, int i2, double& lo,
                                         double& hi) {
   typedef PmlAx<A> X;
-  const int ia = pml_ia<A>(i0, i1, i2);
   const i64 idx = pml_lin(i0, i1, i2);
+  if (INT) {
+    lo = PML_LD(p + idx - X::S);
+    hi = PML_LD(p + idx + X::S);
+    return;
+  }
+  const int ia = pml_ia<A>(i0, i1, i2);
   if (ia > 0) {
     lo = PML_LD(p + idx - X::S);
   } else {
@@ -164,29 +172,32 @@ __device__ __forceinline__ void pml_nb2(const PmlArgs& a,
   }
 }
 
-template <int A>
+template <int A, bool INT>
 __device__ __forceinline__ double pml_d2_at(const PmlArgs& a,
                                             const double* __restrict__ p,
                                             int comp, int i0, int i1, int i2) {
   double lo, hi;
-  pml_nb2<A>(a, p, comp, i0, i1, i2, lo, hi);
+  pml_nb2<A, INT>(a, p, comp, i0, i1, i2, lo, hi);
   const double c = PML_LD(p + pml_lin(i0, i1, i2));
   return ((hi - 2.0 * c) + lo) * PmlAx<A>::INVHH;
 }
 
 // mixed second derivative: constrained d/dA, then unconstrained zero-ghost d/dB
-template <int A, int B>
+template <int A, int B, bool INT>
 __device__ __forceinline__ double pml_d2m_at(const PmlArgs& a,
                                              const double* __restrict__ p,
                                              int comp, int i0, int i1, int i2) {
   typedef PmlAx<B> X;
   const int ib = pml_ia<B>(i0, i1, i2);
   const int e0 = B == 0, e1 = B == 1, e2 = B == 2;
+  // for an interior cell the two points i -/+ e_B keep the cell's (interior)
+  // coordinate along A, so their d/dA needs no boundary handling either
   const double lo =
-      ib > 0 ? pml_d1_at<A>(a, p, comp, i0 - e0, i1 - e1, i2 - e2) : 0.0;
-  const double hi = ib < X::N - 1
-                        ? pml_d1_at<A>(a, p, comp, i0 + e0, i1 + e1, i2 + e2)
-                        : 0.0;
+      (INT || ib > 0)
+          ? pml_d1_at<A, INT>(a, p, comp, i0 - e0, i1 - e1, i2 - e2) : 0.0;
+  const double hi =
+      (INT || ib < X::N - 1)
+          ? pml_d1_at<A, INT>(a, p, comp, i0 + e0, i1 + e1, i2 + e2) : 0.0;
   return (hi - lo) * X::INV2H;
 }
 
@@ -224,6 +235,14 @@ __device__ __forceinline__ double pml_dirichlet(const PmlArgs& a, i64 slot,
   return v;
 }
 
+__device__ __forceinline__ bool pml_is_interior(const PmlCell& c) {
+  bool in = true;
+  if (PML_NDIM >= 1) in = in && c.i0 > 0 && c.i0 < PML_N0 - 1;
+  if (PML_NDIM >= 2) in = in && c.i1 > 0 && c.i1 < PML_N1 - 1;
+  if (PML_NDIM >= 3) in = in && c.i2 > 0 && c.i2 < PML_N2 - 1;
+  return PML_NDIM >= 1 && in;
+}
+
 // ---------------------------------------------------------------------------
 // generated right-hand sides (prelude declares, generator defines below)
 // ---------------------------------------------------------------------------
@@ -256,7 +275,15 @@ __device__ __forceinline__ void pml_stage_cell(const PmlArgs& a,
   }
 
   double K[PML_NDT > 0 ? PML_NDT : 1];
-  pml_rhs_dt(a, P, c, a.t_eval, K);
+  // warps made of interior cells only take the branch-free variant of the
+  // generated right-hand side: every stencil load is unconditional, so the
+  // compiler issues them back to back (memory-level parallelism)
+  const bool interior = pml_is_interior(c);
+  const bool fast = __all_sync(__activemask(), interior);
+  if (fast)
+    pml_rhs_dt<true>(a, P, c, a.t_eval, K);
+  else
+    pml_rhs_dt<false>(a, P, c, a.t_eval, K);
 
 #pragma unroll
   for (int j = 0; j < PML_NDT; ++j) {
@@ -304,7 +331,10 @@ __device__ __forceinline__ void pml_stage_cell(const PmlArgs& a,
   // first stage, whose stencil input is exactly that state
   if (first) {
     double V[PML_NALG + PML_NLAP];
-    pml_rhs_aux(a, P, c, a.t_eval, V);
+    if (fast)
+      pml_rhs_aux<true>(a, P, c, a.t_eval, V);
+    else
+      pml_rhs_aux<false>(a, P, c, a.t_eval, V);
 #pragma unroll
     for (int j = 0; j < PML_NALG; ++j) {
       const int k = PML_ALG_IDX[j];
@@ -365,7 +395,7 @@ extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ)
 #pragma unroll
   for (int k = 0; k < PML_C; ++k) P[k] = a.u + (i64)k * PML_NCELLS;
   double K[PML_NDT > 0 ? PML_NDT : 1];
-  pml_rhs_dt(a, P, c, a.t_eval, K);
+  pml_rhs_dt<false>(a, P, c, a.t_eval, K);
 #pragma unroll
   for (int j = 0; j < PML_NDT; ++j) a.u_out[(i64)j * PML_NCELLS + c.idx] = K[j];
 }
@@ -411,14 +441,14 @@ extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ)
       const double* p = j.y_hat + (i64)q * PML_NCELLS;
       double lo, hi, acc = 0.0;
 #if PML_COORD == 0
-      pml_nb2<0>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
+      pml_nb2<0, false>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
       acc += (lo + hi) * PML_INVHH0;
 #if PML_NDIM >= 2
-      pml_nb2<1>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
+      pml_nb2<1, false>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
       acc += (lo + hi) * PML_INVHH1;
 #endif
 #if PML_NDIM >= 3
-      pml_nb2<2>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
+      pml_nb2<2, false>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
       acc += (lo + hi) * PML_INVHH2;
 #endif
       acc -= PML_LD(j.rhs + (i64)q * PML_NCELLS + c.idx);
@@ -427,25 +457,25 @@ extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ)
       const double r = __ldg(a.coord[0] + c.i0);
       const double r2 = r * r;
       double diag;
-      pml_nb2<0>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
+      pml_nb2<0, false>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
 #if PML_COORD == 3
       const double s = __ldg(a.aux[1] + c.i2), co = __ldg(a.aux[2] + c.i2);
       const double r2s2 = r2 * (s * s);
       acc += (lo + hi) / (PML_H0 * PML_H0) + (hi - lo) / (PML_H0 * r);
-      pml_nb2<1>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
+      pml_nb2<1, false>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
       acc += ((lo + hi) / (PML_H1 * PML_H1)) / r2s2;
-      pml_nb2<2>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
+      pml_nb2<2, false>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
       acc += ((lo + hi) / (PML_H2 * PML_H2) +
               co * (hi - lo) / (2.0 * PML_H2 * s)) / r2;
       diag = 2.0 / (PML_H0 * PML_H0) + 2.0 / ((PML_H1 * PML_H1) * r2s2) +
              2.0 / ((PML_H2 * PML_H2) * r2);
 #else
       acc += (lo + hi) / (PML_H0 * PML_H0) + (hi - lo) / (2.0 * PML_H0 * r);
-      pml_nb2<1>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
+      pml_nb2<1, false>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
       acc += ((lo + hi) / (PML_H1 * PML_H1)) / r2;
       diag = 2.0 / (PML_H0 * PML_H0) + 2.0 / ((PML_H1 * PML_H1) * r2);
 #if PML_COORD == 2
-      pml_nb2<2>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
+      pml_nb2<2, false>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
       acc += (lo + hi) / (PML_H2 * PML_H2);
       diag += 2.0 / (PML_H2 * PML_H2);
 #endif

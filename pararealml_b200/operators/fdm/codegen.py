@@ -122,18 +122,19 @@ class _LeafBuilder:
 
     def D1(self, c, a):
         return self._prim(
-            f"D1_{c}_{a}", f"pml_d1_at<{a}>(a, P[{c}], {c}, c.i0, c.i1, c.i2)"
+            f"D1_{c}_{a}",
+            f"pml_d1_at<{a}, INT>(a, P[{c}], {c}, c.i0, c.i1, c.i2)",
         )
 
     def D2(self, c, a, b=None):
         if b is None or a == b:
             return self._prim(
                 f"D2_{c}_{a}",
-                f"pml_d2_at<{a}>(a, P[{c}], {c}, c.i0, c.i1, c.i2)",
+                f"pml_d2_at<{a}, INT>(a, P[{c}], {c}, c.i0, c.i1, c.i2)",
             )
         return self._prim(
             f"D2M_{c}_{a}_{b}",
-            f"pml_d2m_at<{a}, {b}>(a, P[{c}], {c}, c.i0, c.i1, c.i2)",
+            f"pml_d2m_at<{a}, {b}, INT>(a, P[{c}], {c}, c.i0, c.i1, c.i2)",
         )
 
     def X(self, a):
@@ -379,6 +380,7 @@ def _emit_function(fn_name: str, spec: ProblemSpec, eq_indices: Sequence[int]):
     ]
     body = "\n".join(prim_lines + leaf_lines + out_lines)
     return (
+        "template <bool INT>\n"
         f"__device__ __forceinline__ void {fn_name}(const PmlArgs& a, "
         "const double* const* P, const PmlCell& c, double t, double* out) {\n"
         "  (void)a; (void)P; (void)c; (void)t; (void)out;\n"
@@ -407,6 +409,8 @@ def generate_source(spec: ProblemSpec) -> str:
     alg_idx = [i for i, k in enumerate(kinds) if k == 1]
     lap_idx = [i for i, k in enumerate(kinds) if k == 2]
     block = spec.block or default_block(spec.shape)
+    if os.environ.get("PML_BLOCK"):
+        block = tuple(int(v) for v in os.environ["PML_BLOCK"].split(","))
 
     lines = [
         "// generated by pararealml_b200/operators/fdm/codegen.py",

@@ -60,6 +60,8 @@ class DevicePlan:
         self.spec = spec
         self.source = codegen.generate_source(spec)
         block = spec.block or codegen.default_block(spec.shape)
+        if os.environ.get("PML_BLOCK"):
+            block = tuple(int(v) for v in os.environ["PML_BLOCK"].split(","))
         desc = _native.PlanDesc()
         desc.n_dims = low.n_dims
         shape3 = list(low.shape) + [1] * (3 - low.n_dims)
