@@ -37,9 +37,10 @@ def parse_args():
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    p.add_argument("--grid", type=int, default=int(os.environ.get("PML_BENCH_GRID", "512")))
-    p.add_argument("--equation", default="burgers")
-    p.add_argument("--e2e-steps", type=int, default=4)
+    p.add_argument("--grid", type=int, default=int(os.environ.get("PML_BENCH_GRID", "0")),
+                   help="vertices per axis (0 = the workload's named size)")
+    p.add_argument("--workload", default="burgers_3d", choices=list(WORKLOADS))
+    p.add_argument("--e2e-steps", type=int, default=8)
     p.add_argument("--slice-steps", type=int, default=4,
                    help="fine steps per Parareal time slice")
     p.add_argument("--coarse-ratio", type=int, default=2,
@@ -84,6 +85,103 @@ def burgers_problem(ns, n, n_steps, d_t=None):
     ic = ns.DiscreteInitialCondition(cp, gaussian_y0(n), True)
     ivp = ns.InitialValueProblem(cp, (0.0, n_steps * d_t), ic)
     return ivp, d_t
+
+
+def cahn_hilliard_problem(ns, n, n_steps, d_t=None):
+    """K3: CahnHilliardEquation(3, gamma=0.5) on an n^3 mesh with unit
+    spacing, zero-flux boundaries, uniform random concentration
+    (examples/cahn_hilliard_3d_fdm.py)."""
+    gamma = 0.5
+    eq = ns.CahnHilliardEquation(3, gamma=gamma)
+    mesh = ns.Mesh([(1.0, float(n))] * 3, [1.0] * 3)
+    bc = ns.NeumannBoundaryCondition(
+        lambda x, t: np.zeros((len(x), 2)), is_static=True
+    )
+    cp = ns.ConstrainedProblem(eq, mesh, [(bc, bc)] * 3)
+    rng = np.random.default_rng(0)
+    y0 = np.empty((n, n, n, 2))
+    c = 0.05 * rng.uniform(-1.0, 1.0, (n, n, n))
+    lap = np.zeros_like(c)
+    for a in range(3):
+        p = np.concatenate(
+            [np.take(c, [1], axis=a), c, np.take(c, [-2], axis=a)], axis=a
+        )
+        idx = [slice(None)] * 3
+        lo, mid, hi = list(idx), list(idx), list(idx)
+        lo[a], mid[a], hi[a] = slice(0, -2), slice(1, -1), slice(2, None)
+        lap += p[tuple(hi)] - 2.0 * p[tuple(mid)] + p[tuple(lo)]
+    y0[..., 0] = c
+    y0[..., 1] = c**3 - c - gamma * lap
+    if d_t is None:
+        d_t = 0.05
+    ic = ns.DiscreteInitialCondition(cp, y0, True)
+    return ns.InitialValueProblem(cp, (0.0, n_steps * d_t), ic), d_t
+
+
+def shallow_water_problem(ns, n, n_steps, d_t=None):
+    """K4a: ShallowWaterEquation(0.5) on a polar n x n mesh
+    (examples/shallow_water_polar_fdm.py)."""
+    eq = ns.ShallowWaterEquation(0.5)
+    mesh = ns.Mesh(
+        [(4.0, 11.0), (0.5 * np.pi, 1.5 * np.pi)],
+        [7.0 / (n - 1), np.pi / (n - 1)],
+        ns.CoordinateSystem.POLAR,
+    )
+    bc = ns.NeumannBoundaryCondition(
+        lambda x, t: np.stack(
+            [np.zeros(len(x)), np.full(len(x), np.nan), np.full(len(x), np.nan)],
+            axis=-1,
+        ),
+        is_static=True,
+    )
+    cp = ns.ConstrainedProblem(eq, mesh, [(bc, bc)] * 2)
+    r, th = np.meshgrid(*mesh.vertex_axis_coordinates, indexing="ij")
+    x, y = r * np.cos(th), r * np.sin(th)
+    y0 = np.zeros((n, n, 3))
+    y0[..., 0] = np.exp(-0.5 * ((x + 6.0) ** 2 + (y - 6.0) ** 2) / 0.25) / (
+        2.0 * np.pi * 0.25
+    )
+    if d_t is None:
+        h = min(7.0 / (n - 1), 4.0 * np.pi / (n - 1))
+        d_t = 0.05 * h * h / 0.1
+    ic = ns.DiscreteInitialCondition(cp, y0, True)
+    return ns.InitialValueProblem(cp, (0.0, n_steps * d_t), ic), d_t
+
+
+def diffusion_2d_problem(ns, n, n_steps, d_t=None):
+    """K2 scaled: examples/diffusion_2d_parareal.py on an n x n mesh."""
+    eq = ns.DiffusionEquation(2)
+    h = 10.0 / (n - 1)
+    mesh = ns.Mesh([(0.0, 10.0)] * 2, [h, h])
+    dirichlet = ns.DirichletBoundaryCondition(
+        lambda x, t: np.full((len(x), 1), 1.5), is_static=True
+    )
+    neumann = ns.NeumannBoundaryCondition(
+        lambda x, t: np.zeros((len(x), 1)), is_static=True
+    )
+    cp = ns.ConstrainedProblem(
+        eq, mesh, [(dirichlet, dirichlet), (neumann, neumann)]
+    )
+    x = np.linspace(0.0, 10.0, n)
+    g = np.exp(-0.5 * (x - 5.0) ** 2) / np.sqrt(2.0 * np.pi)
+    y0 = (1000.0 * g[:, None] * g[None, :])[..., None]
+    if d_t is None:
+        d_t = 0.2 * h * h
+    ic = ns.DiscreteInitialCondition(cp, y0, True)
+    return ns.InitialValueProblem(cp, (0.0, n_steps * d_t), ic), d_t
+
+
+# name -> (builder, default vertices per axis, y_dim, spatial dims, label)
+WORKLOADS = {
+    "burgers_3d": (burgers_problem, 512, 3, 3,
+                   "BurgersEquation(3, Re=100), zero-flux boundaries, Gaussian initial condition"),
+    "cahn_hilliard_3d": (cahn_hilliard_problem, 256, 2, 3,
+                         "CahnHilliardEquation(3, gamma=0.5), zero-flux boundaries, random concentration"),
+    "shallow_water_polar": (shallow_water_problem, 4096, 3, 2,
+                            "ShallowWaterEquation(0.5) on a polar mesh, zero-flux height"),
+    "diffusion_2d": (diffusion_2d_problem, 2048, 1, 2,
+                     "DiffusionEquation(2), Dirichlet 1.5 / zero-flux boundaries"),
+}
 
 
 # ---------------------------------------------------------------------------
@@ -269,9 +367,10 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    n = args.grid
-    cells = n**3
-    y_dim = 3
+    builder, n_default, y_dim, dims, label = WORKLOADS[args.workload]
+    n = args.grid or n_default
+    cells = n**dims
+    grid = [n] * dims
     peak, peak_src = peak_hbm()
 
     def barrier():
@@ -282,7 +381,7 @@ def run_b200(args):
     if world == 1:
         # ---- device-resident RK4 steps --------------------------------
         total = args.warmup + args.steps
-        ivp, d_t = burgers_problem(ns, n, total)
+        ivp, d_t = builder(ns, n, total)
         op = FDMOperator(RK4(), ThreePointCentralDifferenceMethod(), d_t)
         cp, t, y0, low, plan = op.prepare(ivp)
         y_dev = dv.upload_state(y0, low.n_cells, low.y_dim)
@@ -310,7 +409,7 @@ def run_b200(args):
         # ---- end to end through FDMOperator.solve (host buffers) -----------
         e2e = None
         if not args.no_e2e:
-            ivp_e, d_t_e = burgers_problem(ns, n, args.e2e_steps)
+            ivp_e, d_t_e = builder(ns, n, args.e2e_steps)
             op_e = FDMOperator(RK4(), ThreePointCentralDifferenceMethod(), d_t_e)
             op_e.solve(ivp_e)  # warm-up (pinned buffers, plan)
             torch.cuda.synchronize()
@@ -331,7 +430,7 @@ def run_b200(args):
             }
             del sol
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and args.workload == "burgers_3d":
             v, secs = cpu_baseline(args.cpu_grid, 2)
             cpu = {
                 "value": v, "unit": UNIT, "cores": 1, "kind": "port",
@@ -339,7 +438,7 @@ def run_b200(args):
                           f"3-D Burgers {args.cpu_grid}^3, 2 steps, {secs:.1f} s, "
                           f"single process ({os.cpu_count()} host cores present)",
             }
-        traffic = load_traffic().get("rk4_step_dram_bytes_512")
+        traffic = load_traffic().get(f"{args.workload}_{n}_rk4_step_dram_bytes")
         line = {
             "metric": METRIC,
             "value": value,
@@ -355,10 +454,11 @@ def run_b200(args):
             "data": "synthetic",
             "config": {
                 "workload": f"FDMOperator(RK4, ThreePointCentralDifferenceMethod) "
-                            f"on BurgersEquation(3, Re=100), {n}^3 mesh, "
-                            "zero-flux boundaries, Gaussian initial condition",
-                "grid": [n, n, n], "y_dim": y_dim, "d_t": d_t,
-                "cache": "state (3.2 GB at 512^3) is larger than L2",
+                            f"on {label}, {'x'.join(str(v) for v in grid)} mesh",
+                "name": args.workload,
+                "grid": grid, "y_dim": y_dim, "d_t": d_t,
+                "cache": f"state ({cells * y_dim * 8 / 1e9:.2f} GB) is larger "
+                         "than the 126 MB L2",
                 "finite": finite,
             },
             "clocks": clocks.summary(),
@@ -383,7 +483,7 @@ def run_b200(args):
     # ---- N > 1: Parareal, one time slice per GPU ----------------------------
     s_steps = args.slice_steps
     total_steps = world * s_steps
-    ivp, d_t = burgers_problem(ns, n, total_steps)
+    ivp, d_t = builder(ns, n, total_steps)
     f = FDMOperator(RK4(), ThreePointCentralDifferenceMethod(), d_t)
     g = FDMOperator(
         ForwardEulerMethod(), ThreePointCentralDifferenceMethod(),
@@ -443,12 +543,14 @@ def run_b200(args):
             "data": "synthetic",
             "config": {
                 "workload": f"PararealOperator(f=FDM RK4 d_t, g=FDM ForwardEuler "
-                            f"{args.coarse_ratio} d_t) on BurgersEquation(3, "
-                            f"Re=100), {n}^3 mesh, {world} time slices x "
-                            f"{s_steps} fine steps, tol {args.parareal_tol}",
-                "grid": [n, n, n], "y_dim": y_dim, "d_t": d_t,
+                            f"{args.coarse_ratio} d_t) on {label}, "
+                            f"{'x'.join(str(v) for v in grid)} mesh, {world} time "
+                            f"slices x {s_steps} fine steps, tol {args.parareal_tol}",
+                "name": args.workload,
+                "grid": grid, "y_dim": y_dim, "d_t": d_t,
                 "parareal_iterations": iterations,
-                "cache": "state (3.2 GB at 512^3) is larger than L2",
+                "cache": f"state ({cells * y_dim * 8 / 1e9:.2f} GB) is larger "
+                         "than the 126 MB L2",
             },
             "clocks": clocks.summary(),
             "roofline": {

@@ -98,8 +98,19 @@ template <int A> __device__ __forceinline__ i64 pml_face(int i0, int i1, int i2)
 #if PML_COHERENT_LOADS
 // single-CTA time loop: data written earlier in the same launch is re-read
 #define PML_LD(p) (*(const volatile double*)(p))
+#define PML_LD_ONCE(p) (*(const volatile double*)(p))
+#define PML_ST(p, v) (*(p) = (v))
 #else
 #define PML_LD(p) __ldg(p)
+// read-once / write-once data (step-start state, accumulator, outputs) is
+// streamed so that L1/L2 keep the stencil input, which is re-read ~7 times
+#if PML_STREAMING
+#define PML_LD_ONCE(p) __ldcs(p)
+#define PML_ST(p, v) __stcs((p), (v))
+#else
+#define PML_LD_ONCE(p) __ldg(p)
+#define PML_ST(p, v) (*(p) = (v))
+#endif
 #endif
 
 template <int A, int SIDE>
@@ -113,15 +124,17 @@ __device__ __forceinline__ double pml_neu(const PmlArgs& a, int comp, int i0,
 
 // first derivative along A at an arbitrary cell: zero ghost cells, boundary
 // planes overwritten by the Neumann value where one exists
-// INT = true: the cell is known to be interior (no axis coordinate on a domain
-// face), all boundary handling compiles away and the loads are unconditional
-template <int A, bool INT>
+// IM = interior mask: bit A set means the cell's coordinate along axis A is known
+// not to lie on a domain face, so the boundary handling of that axis compiles
+// away and its loads are unconditional
+template <int A, int IM>
 __device__ __forceinline__ double pml_d1_at(const PmlArgs& a,
                                             const double* __restrict__ p,
                                             int comp, int i0, int i1, int i2) {
   typedef PmlAx<A> X;
   const i64 idx = pml_lin(i0, i1, i2);
-  if (INT) return (PML_LD(p + idx + X::S) - PML_LD(p + idx - X::S)) * X::INV2H;
+  if ((IM >> A) & 1)
+    return (PML_LD(p + idx + X::S) - PML_LD(p + idx - X::S)) * X::INV2H;
   const int ia = pml_ia<A>(i0, i1, i2);
   const double lo = ia > 0 ? PML_LD(p + idx - X::S) : 0.0;
   const double hi = ia < X::N - 1 ? PML_LD(p + idx + X::S) : 0.0;
@@ -139,14 +152,14 @@ __device__ __forceinline__ double pml_d1_at(const PmlArgs& a,
 
 // neighbour sum / difference helpers with the second-difference ghost rule:
 // ghost = inner neighbour -/+ 2 h g where a Neumann value g exists, else 0
-template <int A, bool INT>
+template <int A, int IM>
 __device__ __forceinline__ void pml_nb2(const PmlArgs& a,
                                         const double* __restrict__ p, int comp,
                                         int i0, int i1, int i2, double& lo,
                                         double& hi) {
   typedef PmlAx<A> X;
   const i64 idx = pml_lin(i0, i1, i2);
-  if (INT) {
+  if ((IM >> A) & 1) {
     lo = PML_LD(p + idx - X::S);
     hi = PML_LD(p + idx + X::S);
     return;
@@ -172,32 +185,33 @@ __device__ __forceinline__ void pml_nb2(const PmlArgs& a,
   }
 }
 
-template <int A, bool INT>
+template <int A, int IM>
 __device__ __forceinline__ double pml_d2_at(const PmlArgs& a,
                                             const double* __restrict__ p,
                                             int comp, int i0, int i1, int i2) {
   double lo, hi;
-  pml_nb2<A, INT>(a, p, comp, i0, i1, i2, lo, hi);
+  pml_nb2<A, IM>(a, p, comp, i0, i1, i2, lo, hi);
   const double c = PML_LD(p + pml_lin(i0, i1, i2));
   return ((hi - 2.0 * c) + lo) * PmlAx<A>::INVHH;
 }
 
 // mixed second derivative: constrained d/dA, then unconstrained zero-ghost d/dB
-template <int A, int B, bool INT>
+template <int A, int B, int IM>
 __device__ __forceinline__ double pml_d2m_at(const PmlArgs& a,
                                              const double* __restrict__ p,
                                              int comp, int i0, int i1, int i2) {
   typedef PmlAx<B> X;
   const int ib = pml_ia<B>(i0, i1, i2);
   const int e0 = B == 0, e1 = B == 1, e2 = B == 2;
-  // for an interior cell the two points i -/+ e_B keep the cell's (interior)
-  // coordinate along A, so their d/dA needs no boundary handling either
+  // the two points i -/+ e_B keep the cell's coordinate along A, so the
+  // interior knowledge about axis A carries over to their d/dA
+  constexpr bool b_in = (IM >> B) & 1;
   const double lo =
-      (INT || ib > 0)
-          ? pml_d1_at<A, INT>(a, p, comp, i0 - e0, i1 - e1, i2 - e2) : 0.0;
+      (b_in || ib > 0)
+          ? pml_d1_at<A, IM>(a, p, comp, i0 - e0, i1 - e1, i2 - e2) : 0.0;
   const double hi =
-      (INT || ib < X::N - 1)
-          ? pml_d1_at<A, INT>(a, p, comp, i0 + e0, i1 + e1, i2 + e2) : 0.0;
+      (b_in || ib < X::N - 1)
+          ? pml_d1_at<A, IM>(a, p, comp, i0 + e0, i1 + e1, i2 + e2) : 0.0;
   return (hi - lo) * X::INV2H;
 }
 
@@ -235,12 +249,18 @@ __device__ __forceinline__ double pml_dirichlet(const PmlArgs& a, i64 slot,
   return v;
 }
 
-__device__ __forceinline__ bool pml_is_interior(const PmlCell& c) {
-  bool in = true;
-  if (PML_NDIM >= 1) in = in && c.i0 > 0 && c.i0 < PML_N0 - 1;
-  if (PML_NDIM >= 2) in = in && c.i1 > 0 && c.i1 < PML_N1 - 1;
-  if (PML_NDIM >= 3) in = in && c.i2 > 0 && c.i2 < PML_N2 - 1;
-  return PML_NDIM >= 1 && in;
+#define PML_IM_ALL ((1 << PML_NDIM) - 1)
+// every axis but the contiguous (last) one: only the two edge lanes of a mesh
+// row then need boundary handling
+#define PML_IM_OUTER (PML_NDIM >= 2 ? (PML_IM_ALL & ~(1 << (PML_NDIM - 1))) : 0)
+
+// bit A set: the cell is not on a face normal to axis A
+__device__ __forceinline__ int pml_interior_mask(const PmlCell& c) {
+  int m = 0;
+  if (PML_NDIM >= 1 && c.i0 > 0 && c.i0 < PML_N0 - 1) m |= 1;
+  if (PML_NDIM >= 2 && c.i1 > 0 && c.i1 < PML_N1 - 1) m |= 2;
+  if (PML_NDIM >= 3 && c.i2 > 0 && c.i2 < PML_N2 - 1) m |= 4;
+  return m;
 }
 
 // ---------------------------------------------------------------------------
@@ -278,38 +298,47 @@ __device__ __forceinline__ void pml_stage_cell(const PmlArgs& a,
   // warps made of interior cells only take the branch-free variant of the
   // generated right-hand side: every stencil load is unconditional, so the
   // compiler issues them back to back (memory-level parallelism)
-  const bool interior = pml_is_interior(c);
-  const bool fast = __all_sync(__activemask(), interior);
-  if (fast)
-    pml_rhs_dt<true>(a, P, c, a.t_eval, K);
+  const int im = pml_interior_mask(c);
+  const unsigned lanes = __activemask();
+  const int path = __all_sync(lanes, im == PML_IM_ALL)
+                       ? 2
+                       : ((PML_IM_OUTER != 0 &&
+                           __all_sync(lanes, (im & PML_IM_OUTER) == PML_IM_OUTER))
+                              ? 1
+                              : 0);
+  if (path == 2)
+    pml_rhs_dt<PML_IM_ALL>(a, P, c, a.t_eval, K);
+  else if (path == 1)
+    pml_rhs_dt<PML_IM_OUTER>(a, P, c, a.t_eval, K);
   else
-    pml_rhs_dt<false>(a, P, c, a.t_eval, K);
+    pml_rhs_dt<0>(a, P, c, a.t_eval, K);
 
 #pragma unroll
   for (int j = 0; j < PML_NDT; ++j) {
     const int k = PML_DT_IDX[j];
     const i64 o = (i64)k * PML_NCELLS + c.idx;
-    const double y0 = first ? PML_LD(P[k] + c.idx) : PML_LD(a.y + o);
+    const double y0 = first ? PML_LD(P[k] + c.idx) : PML_LD_ONCE(a.y + o);
     if (STAGE == PML_FE) {
-      a.y_next[o] = pml_dirichlet(a, a.dir_slot, k, c, y0 + a.dt * K[j]);
+      PML_ST(a.y_next + o, pml_dirichlet(a, a.dir_slot, k, c, y0 + a.dt * K[j]));
     } else if (STAGE == PML_MID1) {
-      a.u_out[o] = pml_dirichlet(a, a.dir_slot, k, c, y0 + (a.dt / 2.0) * K[j]);
+      PML_ST(a.u_out + o, pml_dirichlet(a, a.dir_slot, k, c, y0 + (a.dt / 2.0) * K[j]));
     } else if (STAGE == PML_MID2) {
-      a.y_next[o] = pml_dirichlet(a, a.dir_slot, k, c, y0 + a.dt * K[j]);
+      PML_ST(a.y_next + o, pml_dirichlet(a, a.dir_slot, k, c, y0 + a.dt * K[j]));
     } else {
       const double kk = a.dt * K[j];
       if (STAGE == PML_RK4_1) {
-        a.acc_out[o] = kk;
-        a.u_out[o] = pml_dirichlet(a, a.dir_slot, k, c, y0 + kk / 2.0);
+        PML_ST(a.acc_out + o, kk);
+        PML_ST(a.u_out + o, pml_dirichlet(a, a.dir_slot, k, c, y0 + kk / 2.0));
       } else if (STAGE == PML_RK4_2) {
-        a.acc_out[o] = PML_LD(a.acc_in + o) + 2.0 * kk;
-        a.u_out[o] = pml_dirichlet(a, a.dir_slot, k, c, y0 + kk / 2.0);
+        PML_ST(a.acc_out + o, PML_LD_ONCE(a.acc_in + o) + 2.0 * kk);
+        PML_ST(a.u_out + o, pml_dirichlet(a, a.dir_slot, k, c, y0 + kk / 2.0));
       } else if (STAGE == PML_RK4_3) {
-        a.acc_out[o] = PML_LD(a.acc_in + o) + 2.0 * kk;
-        a.u_out[o] = pml_dirichlet(a, a.dir_slot, k, c, y0 + kk);
+        PML_ST(a.acc_out + o, PML_LD_ONCE(a.acc_in + o) + 2.0 * kk);
+        PML_ST(a.u_out + o, pml_dirichlet(a, a.dir_slot, k, c, y0 + kk));
       } else {
-        a.y_next[o] = pml_dirichlet(a, a.dir_slot, k, c,
-                                    y0 + (PML_LD(a.acc_in + o) + kk) / 6.0);
+        PML_ST(a.y_next + o,
+               pml_dirichlet(a, a.dir_slot, k, c,
+                             y0 + (PML_LD_ONCE(a.acc_in + o) + kk) / 6.0));
       }
     }
   }
@@ -331,10 +360,12 @@ __device__ __forceinline__ void pml_stage_cell(const PmlArgs& a,
   // first stage, whose stencil input is exactly that state
   if (first) {
     double V[PML_NALG + PML_NLAP];
-    if (fast)
-      pml_rhs_aux<true>(a, P, c, a.t_eval, V);
+    if (path == 2)
+      pml_rhs_aux<PML_IM_ALL>(a, P, c, a.t_eval, V);
+    else if (path == 1)
+      pml_rhs_aux<PML_IM_OUTER>(a, P, c, a.t_eval, V);
     else
-      pml_rhs_aux<false>(a, P, c, a.t_eval, V);
+      pml_rhs_aux<0>(a, P, c, a.t_eval, V);
 #pragma unroll
     for (int j = 0; j < PML_NALG; ++j) {
       const int k = PML_ALG_IDX[j];
@@ -370,7 +401,8 @@ __device__ __forceinline__ bool pml_this_cell(PmlCell& c) {
 }
 
 #define PML_STAGE_KERNEL(NAME, STAGE)                                      \
-  extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ)     \
+  extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ,     \
+                                               PML_MIN_BLOCKS)             \
       NAME(const __grid_constant__ PmlArgs a) {                            \
     PmlCell c;                                                             \
     if (!pml_this_cell(c)) return;                                         \
@@ -395,7 +427,7 @@ extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ)
 #pragma unroll
   for (int k = 0; k < PML_C; ++k) P[k] = a.u + (i64)k * PML_NCELLS;
   double K[PML_NDT > 0 ? PML_NDT : 1];
-  pml_rhs_dt<false>(a, P, c, a.t_eval, K);
+  pml_rhs_dt<0>(a, P, c, a.t_eval, K);
 #pragma unroll
   for (int j = 0; j < PML_NDT; ++j) a.u_out[(i64)j * PML_NCELLS + c.idx] = K[j];
 }
@@ -441,14 +473,14 @@ extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ)
       const double* p = j.y_hat + (i64)q * PML_NCELLS;
       double lo, hi, acc = 0.0;
 #if PML_COORD == 0
-      pml_nb2<0, false>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
+      pml_nb2<0, 0>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
       acc += (lo + hi) * PML_INVHH0;
 #if PML_NDIM >= 2
-      pml_nb2<1, false>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
+      pml_nb2<1, 0>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
       acc += (lo + hi) * PML_INVHH1;
 #endif
 #if PML_NDIM >= 3
-      pml_nb2<2, false>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
+      pml_nb2<2, 0>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
       acc += (lo + hi) * PML_INVHH2;
 #endif
       acc -= PML_LD(j.rhs + (i64)q * PML_NCELLS + c.idx);
@@ -457,25 +489,25 @@ extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ)
       const double r = __ldg(a.coord[0] + c.i0);
       const double r2 = r * r;
       double diag;
-      pml_nb2<0, false>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
+      pml_nb2<0, 0>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
 #if PML_COORD == 3
       const double s = __ldg(a.aux[1] + c.i2), co = __ldg(a.aux[2] + c.i2);
       const double r2s2 = r2 * (s * s);
       acc += (lo + hi) / (PML_H0 * PML_H0) + (hi - lo) / (PML_H0 * r);
-      pml_nb2<1, false>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
+      pml_nb2<1, 0>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
       acc += ((lo + hi) / (PML_H1 * PML_H1)) / r2s2;
-      pml_nb2<2, false>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
+      pml_nb2<2, 0>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
       acc += ((lo + hi) / (PML_H2 * PML_H2) +
               co * (hi - lo) / (2.0 * PML_H2 * s)) / r2;
       diag = 2.0 / (PML_H0 * PML_H0) + 2.0 / ((PML_H1 * PML_H1) * r2s2) +
              2.0 / ((PML_H2 * PML_H2) * r2);
 #else
       acc += (lo + hi) / (PML_H0 * PML_H0) + (hi - lo) / (2.0 * PML_H0 * r);
-      pml_nb2<1, false>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
+      pml_nb2<1, 0>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
       acc += ((lo + hi) / (PML_H1 * PML_H1)) / r2;
       diag = 2.0 / (PML_H0 * PML_H0) + 2.0 / ((PML_H1 * PML_H1) * r2);
 #if PML_COORD == 2
-      pml_nb2<2, false>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
+      pml_nb2<2, 0>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
       acc += (lo + hi) / (PML_H2 * PML_H2);
       diag += 2.0 / (PML_H2 * PML_H2);
 #endif

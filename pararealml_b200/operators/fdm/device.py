@@ -4,6 +4,7 @@ streams here.
 """
 import ctypes
 import os
+import warnings
 from typing import Dict, Optional, Sequence
 
 import numpy as np
@@ -22,6 +23,13 @@ CACHE_DIR = os.environ.get(
 
 _PLANS: Dict[str, "DevicePlan"] = {}
 _TOTAL_LAUNCHES = 0
+
+
+def _from_numpy(array: np.ndarray) -> torch.Tensor:
+    """torch view of a (possibly read-only) host array; only ever read."""
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", UserWarning)
+        return torch.from_numpy(np.ascontiguousarray(array))
 
 
 def require_cuda() -> torch.device:
@@ -105,7 +113,7 @@ class DevicePlan:
             pass
 
     def _dev(self, array: np.ndarray) -> torch.Tensor:
-        return torch.from_numpy(np.ascontiguousarray(array)).to(self.device)
+        return _from_numpy(array).to(self.device)
 
     def workspace(self) -> _native.Workspace:
         if self._ws is None:
@@ -294,7 +302,5 @@ def soa_to_aos(soa: torch.Tensor, n_cells: int, y_dim: int, n_states: int = 1,
 def upload_state(y: np.ndarray, n_cells: int, y_dim: int) -> torch.Tensor:
     """Channels-last host state -> component planes on the device."""
     dev = require_cuda()
-    flat = torch.from_numpy(
-        np.ascontiguousarray(y, dtype=np.float64).reshape(-1)
-    )
+    flat = _from_numpy(np.ascontiguousarray(y, dtype=np.float64).reshape(-1))
     return aos_to_soa(flat.to(dev, non_blocking=True), n_cells, y_dim)

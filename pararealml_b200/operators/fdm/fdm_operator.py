@@ -173,9 +173,14 @@ class FDMOperator(Operator):
         fdm_operator.py:56-63), lowering and plan."""
         cp = ivp.constrained_problem
         t = discretize_time_domain(ivp.t_interval, self._d_t)
-        y0 = ivp.initial_condition.discrete_y_0(True)
         low = lowered(cp)
-        if low.n_dims and not low.all_static:
+        ic = ivp.initial_condition
+        dynamic = bool(low.n_dims and not low.all_static)
+        view = getattr(ic, "discrete_y_0_view", None)
+        y0 = None if (dynamic or view is None) else view(True)
+        if y0 is None:
+            y0 = ic.discrete_y_0(True)
+        if dynamic:
             apply_dirichlet_host(cp, y0, float(t[0]))
         plan = self._plan_for(cp, low, y0)
         return cp, t, y0, low, plan
@@ -207,6 +212,10 @@ class FDMOperator(Operator):
         y_prev = dv.upload_state(y0, low.n_cells, low.y_dim)
 
         chunk = max(1, min(n_steps, TRAJECTORY_CHUNK_BYTES // (state * 8)))
+        if state * 8 >= (64 << 20) and n_steps >= 2:
+            # large states: several chunks so that the device-to-host copy of
+            # one chunk overlaps the computation of the next
+            chunk = min(chunk, max(1, -(-n_steps // 4)))
         n_buf = 1 if chunk >= n_steps else 2
         f64 = dict(dtype=torch.float64, device=plan.device)
         bufs = [torch.empty((chunk, state), **f64) for _ in range(n_buf)]
