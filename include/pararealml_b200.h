@@ -27,6 +27,9 @@ typedef struct pml_plan_desc {
   int y_dim;        /* components of y */
   int n_dt, n_alg, n_lap; /* equations per LHS kind (differential_equation.py:140-149) */
   int block[3];     /* thread block shape the source was generated for */
+  int fused;        /* 1: the source has the fused stage-pair kernels */
+  int fused_block[2]; /* their thread block (contiguous axis, axis 1) */
+  int fused_zc;     /* planes of the marching axis per thread block */
 } pml_plan_desc;
 
 /* NaN-coded boundary tables and 1-D coordinate vectors (device pointers).

@@ -31,6 +31,9 @@ class PlanDesc(Structure):
         ("n_alg", c_int),
         ("n_lap", c_int),
         ("block", c_int * 3),
+        ("fused", c_int),
+        ("fused_block", c_int * 2),
+        ("fused_zc", c_int),
     ]
 
 

@@ -122,22 +122,41 @@ __device__ __forceinline__ double pml_neu(const PmlArgs& a, int comp, int i0,
                pml_face<A>(i0, i1, i2) * PML_C + comp);
 }
 
+// ---------------------------------------------------------------------------
+// stencil sources: where the primitives read the field from
+// ---------------------------------------------------------------------------
+// component planes in global memory
+struct PmlGlobalSrc {
+  const double* const* P;
+  __device__ __forceinline__ double at(int comp, int i0, int i1, int i2) const {
+    return PML_LD(P[comp] + pml_lin(i0, i1, i2));
+  }
+};
+
+// one plane (the Jacobi state of a single component)
+struct PmlPlaneSrc {
+  const double* p;
+  __device__ __forceinline__ double at(int, int i0, int i1, int i2) const {
+    return PML_LD(p + pml_lin(i0, i1, i2));
+  }
+};
+
 // first derivative along A at an arbitrary cell: zero ghost cells, boundary
-// planes overwritten by the Neumann value where one exists
+// planes overwritten by the Neumann value where one exists.
 // IM = interior mask: bit A set means the cell's coordinate along axis A is known
 // not to lie on a domain face, so the boundary handling of that axis compiles
 // away and its loads are unconditional
-template <int A, int IM>
-__device__ __forceinline__ double pml_d1_at(const PmlArgs& a,
-                                            const double* __restrict__ p,
+template <int A, int IM, class SRC>
+__device__ __forceinline__ double pml_d1_at(const PmlArgs& a, const SRC& s,
                                             int comp, int i0, int i1, int i2) {
   typedef PmlAx<A> X;
-  const i64 idx = pml_lin(i0, i1, i2);
+  constexpr int e0 = A == 0, e1 = A == 1, e2 = A == 2;
   if ((IM >> A) & 1)
-    return (PML_LD(p + idx + X::S) - PML_LD(p + idx - X::S)) * X::INV2H;
+    return (s.at(comp, i0 + e0, i1 + e1, i2 + e2) -
+            s.at(comp, i0 - e0, i1 - e1, i2 - e2)) * X::INV2H;
   const int ia = pml_ia<A>(i0, i1, i2);
-  const double lo = ia > 0 ? PML_LD(p + idx - X::S) : 0.0;
-  const double hi = ia < X::N - 1 ? PML_LD(p + idx + X::S) : 0.0;
+  const double lo = ia > 0 ? s.at(comp, i0 - e0, i1 - e1, i2 - e2) : 0.0;
+  const double hi = ia < X::N - 1 ? s.at(comp, i0 + e0, i1 + e1, i2 + e2) : 0.0;
   double d = (hi - lo) * X::INV2H;
   if (((PML_NEU_MASK >> (A * 2)) & 1) && ia == 0) {
     const double g = pml_neu<A, 0>(a, comp, i0, i1, i2);
@@ -150,68 +169,65 @@ __device__ __forceinline__ double pml_d1_at(const PmlArgs& a,
   return d;
 }
 
-// neighbour sum / difference helpers with the second-difference ghost rule:
+// neighbour pair with the second-difference ghost rule:
 // ghost = inner neighbour -/+ 2 h g where a Neumann value g exists, else 0
-template <int A, int IM>
-__device__ __forceinline__ void pml_nb2(const PmlArgs& a,
-                                        const double* __restrict__ p, int comp,
+template <int A, int IM, class SRC>
+__device__ __forceinline__ void pml_nb2(const PmlArgs& a, const SRC& s, int comp,
                                         int i0, int i1, int i2, double& lo,
                                         double& hi) {
   typedef PmlAx<A> X;
-  const i64 idx = pml_lin(i0, i1, i2);
+  constexpr int e0 = A == 0, e1 = A == 1, e2 = A == 2;
   if ((IM >> A) & 1) {
-    lo = PML_LD(p + idx - X::S);
-    hi = PML_LD(p + idx + X::S);
+    lo = s.at(comp, i0 - e0, i1 - e1, i2 - e2);
+    hi = s.at(comp, i0 + e0, i1 + e1, i2 + e2);
     return;
   }
   const int ia = pml_ia<A>(i0, i1, i2);
   if (ia > 0) {
-    lo = PML_LD(p + idx - X::S);
+    lo = s.at(comp, i0 - e0, i1 - e1, i2 - e2);
   } else {
     lo = 0.0;
     if ((PML_NEU_MASK >> (A * 2)) & 1) {
       const double g = pml_neu<A, 0>(a, comp, i0, i1, i2);
-      if (g == g) lo = PML_LD(p + idx + X::S) + (-2.0 * X::H) * g;
+      if (g == g) lo = s.at(comp, i0 + e0, i1 + e1, i2 + e2) + (-2.0 * X::H) * g;
     }
   }
   if (ia < X::N - 1) {
-    hi = PML_LD(p + idx + X::S);
+    hi = s.at(comp, i0 + e0, i1 + e1, i2 + e2);
   } else {
     hi = 0.0;
     if ((PML_NEU_MASK >> (A * 2 + 1)) & 1) {
       const double g = pml_neu<A, 1>(a, comp, i0, i1, i2);
-      if (g == g) hi = PML_LD(p + idx - X::S) + (2.0 * X::H) * g;
+      if (g == g) hi = s.at(comp, i0 - e0, i1 - e1, i2 - e2) + (2.0 * X::H) * g;
     }
   }
 }
 
-template <int A, int IM>
-__device__ __forceinline__ double pml_d2_at(const PmlArgs& a,
-                                            const double* __restrict__ p,
+template <int A, int IM, class SRC>
+__device__ __forceinline__ double pml_d2_at(const PmlArgs& a, const SRC& s,
                                             int comp, int i0, int i1, int i2) {
   double lo, hi;
-  pml_nb2<A, IM>(a, p, comp, i0, i1, i2, lo, hi);
-  const double c = PML_LD(p + pml_lin(i0, i1, i2));
+  pml_nb2<A, IM>(a, s, comp, i0, i1, i2, lo, hi);
+  const double c = s.at(comp, i0, i1, i2);
   return ((hi - 2.0 * c) + lo) * PmlAx<A>::INVHH;
 }
 
 // mixed second derivative: constrained d/dA, then unconstrained zero-ghost d/dB
-template <int A, int B, int IM>
-__device__ __forceinline__ double pml_d2m_at(const PmlArgs& a,
-                                             const double* __restrict__ p,
+template <int A, int B, int IM, class SRC>
+__device__ __forceinline__ double pml_d2m_at(const PmlArgs& a, const SRC& s,
                                              int comp, int i0, int i1, int i2) {
   typedef PmlAx<B> X;
   const int ib = pml_ia<B>(i0, i1, i2);
-  const int e0 = B == 0, e1 = B == 1, e2 = B == 2;
+  constexpr int e0 = B == 0, e1 = B == 1, e2 = B == 2;
   // the two points i -/+ e_B keep the cell's coordinate along A, so the
   // interior knowledge about axis A carries over to their d/dA
   constexpr bool b_in = (IM >> B) & 1;
   const double lo =
       (b_in || ib > 0)
-          ? pml_d1_at<A, IM>(a, p, comp, i0 - e0, i1 - e1, i2 - e2) : 0.0;
+          ? pml_d1_at<A, IM>(a, s, comp, i0 - e0, i1 - e1, i2 - e2) : 0.0;
   const double hi =
       (b_in || ib < X::N - 1)
-          ? pml_d1_at<A, IM>(a, p, comp, i0 + e0, i1 + e1, i2 + e2) : 0.0;
+          ? pml_d1_at<A, IM>(a, s, comp, i0 + e0, i1 + e1, i2 + e2) : 0.0;
   return (hi - lo) * X::INV2H;
 }
 
@@ -281,11 +297,74 @@ enum {
   PML_RK4_4 = 6   // K = dt f(t+dt, u);   y+ = c_f(y + (acc + K)/6)
 };
 
+// which variant of the generated right-hand side a warp runs: 2 = every lane is
+// an interior cell (branch-free, all stencil loads unconditional so they issue
+// back to back), 1 = interior along all but the contiguous axis, 0 = general.
+// Must be called by all 32 lanes; inactive lanes do not constrain the choice.
+__device__ __forceinline__ int pml_warp_path(bool active, const PmlCell& c) {
+  const int im = active ? pml_interior_mask(c) : PML_IM_ALL;
+  if (__all_sync(0xffffffffu, im == PML_IM_ALL)) return 2;
+  if (PML_IM_OUTER != 0 &&
+      __all_sync(0xffffffffu, (im & PML_IM_OUTER) == PML_IM_OUTER))
+    return 1;
+  return 0;
+}
+
+template <class SRC>
+__device__ __forceinline__ void pml_eval_dt(int path, const PmlArgs& a,
+                                            const SRC& src, const PmlCell& c,
+                                            double t, double* K) {
+  if (path == 2)
+    pml_rhs_dt<PML_IM_ALL>(a, src, c, t, K);
+  else if (path == 1)
+    pml_rhs_dt<PML_IM_OUTER>(a, src, c, t, K);
+  else
+    pml_rhs_dt<0>(a, src, c, t, K);
+}
+
+template <class SRC>
+__device__ __forceinline__ void pml_eval_aux(int path, const PmlArgs& a,
+                                             const SRC& src, const PmlCell& c,
+                                             double t, double* V) {
+  if (path == 2)
+    pml_rhs_aux<PML_IM_ALL>(a, src, c, t, V);
+  else if (path == 1)
+    pml_rhs_aux<PML_IM_OUTER>(a, src, c, t, V);
+  else
+    pml_rhs_aux<0>(a, src, c, t, V);
+}
+
+// algebraic (LHS.Y) and Poisson (LHS.Y_LAPLACIAN) right-hand sides use the
+// step-start time and state (fdm_operator.py:127-161): they are evaluated in
+// the first stage, whose stencil input is exactly that state
+template <class SRC>
+__device__ __forceinline__ void pml_first_stage_extras(int path,
+                                                       const PmlArgs& a,
+                                                       const SRC& src,
+                                                       const PmlCell& c) {
+#if PML_NALG + PML_NLAP > 0
+  double V[PML_NALG + PML_NLAP];
+  pml_eval_aux(path, a, src, c, a.t_eval, V);
+#pragma unroll
+  for (int j = 0; j < PML_NALG; ++j) {
+    const int k = PML_ALG_IDX[j];
+    a.y_next[(i64)k * PML_NCELLS + c.idx] =
+        pml_dirichlet(a, a.dir_slot_full, k, c, V[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < PML_NLAP; ++j)
+    a.lap_rhs[(i64)j * PML_NCELLS + c.idx] = V[PML_NALG + j];
+#endif
+}
+
 template <int STAGE>
-__device__ __forceinline__ void pml_stage_cell(const PmlArgs& a,
+__device__ __forceinline__ void pml_stage_cell(const PmlArgs& a, bool active,
                                                const PmlCell& c) {
   constexpr bool first = STAGE == PML_FE || STAGE == PML_MID1 || STAGE == PML_RK4_1;
   constexpr bool last = STAGE == PML_FE || STAGE == PML_MID2 || STAGE == PML_RK4_4;
+
+  const int path = pml_warp_path(active, c);
+  if (!active) return;
 
   const double* P[PML_C];
 #pragma unroll
@@ -293,25 +372,10 @@ __device__ __forceinline__ void pml_stage_cell(const PmlArgs& a,
     const bool from_y = first || (PML_PASSTHROUGH && PML_KIND[k] != 0);
     P[k] = (from_y ? a.y : a.u) + (i64)k * PML_NCELLS;
   }
+  const PmlGlobalSrc src{P};
 
   double K[PML_NDT > 0 ? PML_NDT : 1];
-  // warps made of interior cells only take the branch-free variant of the
-  // generated right-hand side: every stencil load is unconditional, so the
-  // compiler issues them back to back (memory-level parallelism)
-  const int im = pml_interior_mask(c);
-  const unsigned lanes = __activemask();
-  const int path = __all_sync(lanes, im == PML_IM_ALL)
-                       ? 2
-                       : ((PML_IM_OUTER != 0 &&
-                           __all_sync(lanes, (im & PML_IM_OUTER) == PML_IM_OUTER))
-                              ? 1
-                              : 0);
-  if (path == 2)
-    pml_rhs_dt<PML_IM_ALL>(a, P, c, a.t_eval, K);
-  else if (path == 1)
-    pml_rhs_dt<PML_IM_OUTER>(a, P, c, a.t_eval, K);
-  else
-    pml_rhs_dt<0>(a, P, c, a.t_eval, K);
+  pml_eval_dt(path, a, src, c, a.t_eval, K);
 
 #pragma unroll
   for (int j = 0; j < PML_NDT; ++j) {
@@ -355,27 +419,7 @@ __device__ __forceinline__ void pml_stage_cell(const PmlArgs& a,
       a.u_out[o] = pml_dirichlet(a, a.dir_slot, k, c, PML_LD(a.y + o));
     }
   }
-  // algebraic (LHS.Y) and Poisson (LHS.Y_LAPLACIAN) right-hand sides use the
-  // step-start time and state (fdm_operator.py:127-161): evaluate them in the
-  // first stage, whose stencil input is exactly that state
-  if (first) {
-    double V[PML_NALG + PML_NLAP];
-    if (path == 2)
-      pml_rhs_aux<PML_IM_ALL>(a, P, c, a.t_eval, V);
-    else if (path == 1)
-      pml_rhs_aux<PML_IM_OUTER>(a, P, c, a.t_eval, V);
-    else
-      pml_rhs_aux<0>(a, P, c, a.t_eval, V);
-#pragma unroll
-    for (int j = 0; j < PML_NALG; ++j) {
-      const int k = PML_ALG_IDX[j];
-      a.y_next[(i64)k * PML_NCELLS + c.idx] =
-          pml_dirichlet(a, a.dir_slot_full, k, c, V[j]);
-    }
-#pragma unroll
-    for (int j = 0; j < PML_NLAP; ++j)
-      a.lap_rhs[(i64)j * PML_NCELLS + c.idx] = V[PML_NALG + j];
-  }
+  if (first) pml_first_stage_extras(path, a, src, c);
 #endif
 }
 
@@ -405,8 +449,8 @@ __device__ __forceinline__ bool pml_this_cell(PmlCell& c) {
                                                PML_MIN_BLOCKS)             \
       NAME(const __grid_constant__ PmlArgs a) {                            \
     PmlCell c;                                                             \
-    if (!pml_this_cell(c)) return;                                         \
-    pml_stage_cell<STAGE>(a, c);                                           \
+    const bool active = pml_this_cell(c);                                  \
+    pml_stage_cell<STAGE>(a, active, c);                                   \
   }
 
 PML_STAGE_KERNEL(pml_stage_fe, PML_FE)
@@ -416,6 +460,215 @@ PML_STAGE_KERNEL(pml_stage_rk4_1, PML_RK4_1)
 PML_STAGE_KERNEL(pml_stage_rk4_2, PML_RK4_2)
 PML_STAGE_KERNEL(pml_stage_rk4_3, PML_RK4_3)
 PML_STAGE_KERNEL(pml_stage_rk4_4, PML_RK4_4)
+
+// ---------------------------------------------------------------------------
+// Fused stage pairs: temporal blocking along the slowest mesh axis.
+//
+// One launch performs two consecutive stages (RK4 1+2, RK4 3+4 or midpoint 1+2).
+// A thread block owns a tile of the in-plane axes plus a one-cell halo ring
+// (PML_FBX x PML_FBY threads <-> halo'd tile cells) and marches along axis 0
+// over PML_FZC planes.  Stage A is evaluated for every cell of the halo'd tile
+// from global memory and its result u_A is written to a 4-slot ring of planes in
+// shared memory; one plane behind, stage B is evaluated for the tile's own cells
+// with all its stencil reads served from that ring.  The intermediate state
+// never goes to HBM: RK4 costs 7 C instead of 17 C doubles of traffic per
+// cell-step at the price of recomputing stage A on the halo ring.
+// Arithmetic per cell is the same sequence of operations as in the unfused
+// stage kernels above.
+// ---------------------------------------------------------------------------
+#if PML_FUSED
+struct PmlFusedArgs {
+  PmlArgs s;        // stage A: input planes, time, table slots; all outputs
+  double t_eval_b;  // stage B evaluation time
+  i64 neu_slot_b;   // stage B table slots
+  i64 dir_slot_b;
+};
+
+#if PML_NDIM == 3
+#define PML_RPLANE (PML_FBX * PML_FBY)
+#else
+#define PML_RPLANE (PML_FBX)
+#endif
+
+// stage-A results of the last four planes, in shared memory
+struct PmlRingSrc {
+  const double* ring;  // [4][C][PML_RPLANE]
+  const double* y;     // passthrough components are read from the state itself
+  int o1, o2;          // mesh coordinates of the ring's first in-plane cell
+  __device__ __forceinline__ double at(int comp, int i0, int i1, int i2) const {
+    if (PML_PASSTHROUGH && PML_KIND[comp] != 0)
+      return PML_LD(y + (i64)comp * PML_NCELLS + pml_lin(i0, i1, i2));
+#if PML_NDIM == 3
+    return ring[((i0 & 3) * PML_C + comp) * PML_RPLANE + (i1 - o1) * PML_FBX +
+                (i2 - o2)];
+#else
+    return ring[((i0 & 3) * PML_C + comp) * PML_RPLANE + (i1 - o1)];
+#endif
+  }
+};
+
+enum { PML_F_RK4_12 = 0, PML_F_RK4_34 = 1, PML_F_MID = 2 };
+
+template <int MODE>
+__device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
+                                               double* ring) {
+  const PmlArgs& a = f.s;
+  constexpr bool first = MODE != PML_F_RK4_34;  // stage A reads y itself
+  const int tx = threadIdx.x;
+#if PML_NDIM == 3
+  const int ty = threadIdx.y;
+  const int o2 = blockIdx.x * (PML_FBX - 2) - 1;
+  const int o1 = blockIdx.y * (PML_FBY - 2) - 1;
+  const int i2 = o2 + tx, i1 = o1 + ty;
+  const bool in_plane = i1 >= 0 && i1 < PML_N1 && i2 >= 0 && i2 < PML_N2;
+  const bool owner = in_plane && tx >= 1 && tx <= PML_FBX - 2 && ty >= 1 &&
+                     ty <= PML_FBY - 2;
+  const int rcell = ty * PML_FBX + tx;
+  const int chunk = blockIdx.z;
+#else
+  const int o1 = blockIdx.x * (PML_FBX - 2) - 1, o2 = 0;
+  const int i1 = o1 + tx, i2 = 0;
+  const bool in_plane = i1 >= 0 && i1 < PML_N1;
+  const bool owner = in_plane && tx >= 1 && tx <= PML_FBX - 2;
+  const int rcell = tx;
+  const int chunk = blockIdx.y;
+#endif
+  const int z_begin = chunk * PML_FZC;
+  const int z_end = min(z_begin + PML_FZC, PML_N0);
+
+  PmlArgs b = a;  // stage B sees its own time and table slots
+  b.t_eval = f.t_eval_b;
+  b.neu_slot = f.neu_slot_b;
+  b.dir_slot = f.dir_slot_b;
+
+  const double* P[PML_C];
+#pragma unroll
+  for (int k = 0; k < PML_C; ++k) {
+    const bool from_y = first || (PML_PASSTHROUGH && PML_KIND[k] != 0);
+    P[k] = (from_y ? a.y : a.u) + (i64)k * PML_NCELLS;
+  }
+  const PmlGlobalSrc gsrc{P};
+  const PmlRingSrc rsrc{ring, a.y, o1, o2};
+
+  constexpr int NK = PML_NDT > 0 ? PML_NDT : 1;
+  double ka_prev[NK], y_prev[NK];
+#pragma unroll
+  for (int j = 0; j < NK; ++j) ka_prev[j] = y_prev[j] = 0.0;
+
+  for (int z = max(z_begin - 1, 0); z <= z_end; ++z) {
+    // ---- stage A on plane z (halo'd tile) --------------------------------
+    double ka_new[NK], y_new[NK];
+#pragma unroll
+    for (int j = 0; j < NK; ++j) ka_new[j] = y_new[j] = 0.0;
+    {
+      const bool active = in_plane && z < PML_N0;
+      PmlCell c;
+      c.i0 = z;
+      c.i1 = i1;
+      c.i2 = i2;
+      c.idx = pml_lin(z, i1, i2);
+      const int path = pml_warp_path(active, c);
+      if (active) {
+        double K[NK];
+        pml_eval_dt(path, a, gsrc, c, a.t_eval, K);
+        double* slot = ring + (i64)((z & 3) * PML_C) * PML_RPLANE + rcell;
+#pragma unroll
+        for (int j = 0; j < PML_NDT; ++j) {
+          const int k = PML_DT_IDX[j];
+          const i64 o = (i64)k * PML_NCELLS + c.idx;
+          const double y0 = first ? PML_LD(P[k] + c.idx) : PML_LD(a.y + o);
+          double ua;
+          if (MODE == PML_F_MID) {
+            ua = y0 + (a.dt / 2.0) * K[j];
+            ka_new[j] = 0.0;
+          } else {
+            const double kk = a.dt * K[j];
+            ua = MODE == PML_F_RK4_12 ? y0 + kk / 2.0 : y0 + kk;
+            ka_new[j] = kk;
+          }
+          y_new[j] = y0;
+          slot[k * PML_RPLANE] = pml_dirichlet(a, a.dir_slot, k, c, ua);
+        }
+#if PML_NALG + PML_NLAP > 0
+        if (!PML_PASSTHROUGH) {
+#pragma unroll
+          for (int k = 0; k < PML_C; ++k) {
+            if (PML_KIND[k] == 0) continue;
+            slot[k * PML_RPLANE] = pml_dirichlet(
+                a, a.dir_slot, k, c, PML_LD(a.y + (i64)k * PML_NCELLS + c.idx));
+          }
+        }
+        if (first && owner && z >= z_begin && z < z_end)
+          pml_first_stage_extras(path, a, gsrc, c);
+#endif
+      }
+    }
+    __syncthreads();
+    // ---- stage B on plane z - 1 (tile cells), stencil reads from the ring --
+    {
+      const int zz = z - 1;
+      const bool active = owner && zz >= z_begin && zz < z_end;
+      PmlCell c;
+      c.i0 = zz;
+      c.i1 = i1;
+      c.i2 = i2;
+      c.idx = pml_lin(zz, i1, i2);
+      const int path = pml_warp_path(active, c);
+      if (active) {
+        double K[NK];
+        pml_eval_dt(path, b, rsrc, c, b.t_eval, K);
+#pragma unroll
+        for (int j = 0; j < PML_NDT; ++j) {
+          const int k = PML_DT_IDX[j];
+          const i64 o = (i64)k * PML_NCELLS + c.idx;
+          if (MODE == PML_F_RK4_12) {
+            const double kk = b.dt * K[j];
+            PML_ST(b.acc_out + o, ka_prev[j] + 2.0 * kk);
+            PML_ST(b.u_out + o,
+                   pml_dirichlet(b, b.dir_slot, k, c, y_prev[j] + kk / 2.0));
+          } else if (MODE == PML_F_RK4_34) {
+            const double kk = b.dt * K[j];
+            const double acc = PML_LD_ONCE(b.acc_in + o) + 2.0 * ka_prev[j];
+            PML_ST(b.y_next + o, pml_dirichlet(b, b.dir_slot, k, c,
+                                               y_prev[j] + (acc + kk) / 6.0));
+          } else {
+            PML_ST(b.y_next + o, pml_dirichlet(b, b.dir_slot, k, c,
+                                               y_prev[j] + b.dt * K[j]));
+          }
+        }
+#if PML_NALG + PML_NLAP > 0
+        if (MODE == PML_F_RK4_12 && !PML_PASSTHROUGH) {
+#pragma unroll
+          for (int k = 0; k < PML_C; ++k) {
+            if (PML_KIND[k] == 0) continue;
+            const i64 o = (i64)k * PML_NCELLS + c.idx;
+            b.u_out[o] = pml_dirichlet(b, b.dir_slot, k, c, PML_LD(b.y + o));
+          }
+        }
+#endif
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NK; ++j) {
+      ka_prev[j] = ka_new[j];
+      y_prev[j] = y_new[j];
+    }
+    // no second barrier: the slot stage A writes next, (z + 1) & 3, is not
+    // among the three slots (z - 2, z - 1, z) a lagging warp may still read
+  }
+}
+
+#define PML_FUSED_KERNEL(NAME, MODE)                                           \
+  extern "C" __global__ void __launch_bounds__(PML_FBX* PML_FBY, PML_FMIN_BLOCKS) \
+      NAME(const __grid_constant__ PmlFusedArgs f) {                          \
+    extern __shared__ double pml_ring[];                                       \
+    pml_fused_body<MODE>(f, pml_ring);                                         \
+  }
+
+PML_FUSED_KERNEL(pml_fused_rk4_12, PML_F_RK4_12)
+PML_FUSED_KERNEL(pml_fused_rk4_34, PML_F_RK4_34)
+PML_FUSED_KERNEL(pml_fused_mid, PML_F_MID)
+#endif  // PML_FUSED
 
 // raw right-hand side evaluation (the NumPy-in / NumPy-out differentiator entry
 // points gradient/hessian/divergence/curl/laplacian are served by this kernel)
@@ -427,7 +680,7 @@ extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ)
 #pragma unroll
   for (int k = 0; k < PML_C; ++k) P[k] = a.u + (i64)k * PML_NCELLS;
   double K[PML_NDT > 0 ? PML_NDT : 1];
-  pml_rhs_dt<0>(a, P, c, a.t_eval, K);
+  pml_rhs_dt<0>(a, PmlGlobalSrc{P}, c, a.t_eval, K);
 #pragma unroll
   for (int j = 0; j < PML_NDT; ++j) a.u_out[(i64)j * PML_NCELLS + c.idx] = K[j];
 }
@@ -471,16 +724,17 @@ extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ)
     for (int q = 0; q < PML_NLAP; ++q) {
       const int comp = PML_LAP_IDX[q];
       const double* p = j.y_hat + (i64)q * PML_NCELLS;
+      const PmlPlaneSrc ps{p};
       double lo, hi, acc = 0.0;
 #if PML_COORD == 0
-      pml_nb2<0, 0>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
+      pml_nb2<0, 0>(a, ps, comp, c.i0, c.i1, c.i2, lo, hi);
       acc += (lo + hi) * PML_INVHH0;
 #if PML_NDIM >= 2
-      pml_nb2<1, 0>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
+      pml_nb2<1, 0>(a, ps, comp, c.i0, c.i1, c.i2, lo, hi);
       acc += (lo + hi) * PML_INVHH1;
 #endif
 #if PML_NDIM >= 3
-      pml_nb2<2, 0>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
+      pml_nb2<2, 0>(a, ps, comp, c.i0, c.i1, c.i2, lo, hi);
       acc += (lo + hi) * PML_INVHH2;
 #endif
       acc -= PML_LD(j.rhs + (i64)q * PML_NCELLS + c.idx);
@@ -489,25 +743,25 @@ extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ)
       const double r = __ldg(a.coord[0] + c.i0);
       const double r2 = r * r;
       double diag;
-      pml_nb2<0, 0>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
+      pml_nb2<0, 0>(a, ps, comp, c.i0, c.i1, c.i2, lo, hi);
 #if PML_COORD == 3
       const double s = __ldg(a.aux[1] + c.i2), co = __ldg(a.aux[2] + c.i2);
       const double r2s2 = r2 * (s * s);
       acc += (lo + hi) / (PML_H0 * PML_H0) + (hi - lo) / (PML_H0 * r);
-      pml_nb2<1, 0>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
+      pml_nb2<1, 0>(a, ps, comp, c.i0, c.i1, c.i2, lo, hi);
       acc += ((lo + hi) / (PML_H1 * PML_H1)) / r2s2;
-      pml_nb2<2, 0>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
+      pml_nb2<2, 0>(a, ps, comp, c.i0, c.i1, c.i2, lo, hi);
       acc += ((lo + hi) / (PML_H2 * PML_H2) +
               co * (hi - lo) / (2.0 * PML_H2 * s)) / r2;
       diag = 2.0 / (PML_H0 * PML_H0) + 2.0 / ((PML_H1 * PML_H1) * r2s2) +
              2.0 / ((PML_H2 * PML_H2) * r2);
 #else
       acc += (lo + hi) / (PML_H0 * PML_H0) + (hi - lo) / (2.0 * PML_H0 * r);
-      pml_nb2<1, 0>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
+      pml_nb2<1, 0>(a, ps, comp, c.i0, c.i1, c.i2, lo, hi);
       acc += ((lo + hi) / (PML_H1 * PML_H1)) / r2;
       diag = 2.0 / (PML_H0 * PML_H0) + 2.0 / ((PML_H1 * PML_H1) * r2);
 #if PML_COORD == 2
-      pml_nb2<2, 0>(a, p, comp, c.i0, c.i1, c.i2, lo, hi);
+      pml_nb2<2, 0>(a, ps, comp, c.i0, c.i1, c.i2, lo, hi);
       acc += (lo + hi) / (PML_H2 * PML_H2);
       diag += 2.0 / (PML_H2 * PML_H2);
 #endif

@@ -48,6 +48,7 @@ struct Driver {
                            unsigned, unsigned, unsigned, CUstream, void**,
                            void**) = nullptr;
   CUresult (*getErrorString)(CUresult, const char**) = nullptr;
+  CUresult (*funcSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
   bool ready = false;
 };
 Driver g_drv;
@@ -64,6 +65,7 @@ int load_driver() {
       {"cuModuleGetFunction", (void**)&g_drv.moduleGetFunction},
       {"cuLaunchKernel", (void**)&g_drv.launchKernel},
       {"cuGetErrorString", (void**)&g_drv.getErrorString},
+      {"cuFuncSetAttribute", (void**)&g_drv.funcSetAttribute},
   };
   for (auto& s : syms) {
     cudaDriverEntryPointQueryResult q;
@@ -107,6 +109,13 @@ struct PmlArgs {
   long long dir_stride[6];
   const double* coord[3];
   const double* aux[4];
+};
+
+struct PmlFusedArgs {
+  PmlArgs s;
+  double t_eval_b;
+  long long neu_slot_b;
+  long long dir_slot_b;
 };
 
 struct PmlJacobiArgs {
@@ -168,6 +177,9 @@ struct pml_plan {
   pml_plan_desc desc;
   CUmodule module = nullptr;
   CUfunction stage[7] = {};
+  CUfunction fused[3] = {};  // rk4 1+2, rk4 3+4, midpoint 1+2
+  dim3 fgrid, fblock;
+  unsigned fsmem = 0;
   CUfunction eval_rhs = nullptr;
   CUfunction jac_init = nullptr, jac_sweep = nullptr, jac_check = nullptr,
              jac_store = nullptr;
@@ -302,6 +314,33 @@ int pml_plan_create(const char* source, const pml_plan_desc* desc,
       return fail(m);
     }
   }
+  if (desc->fused) {
+    static const char* fnames[3] = {"pml_fused_rk4_12", "pml_fused_rk4_34",
+                                    "pml_fused_mid"};
+    const int fbx = desc->fused_block[0], fby = desc->fused_block[1];
+    p->fsmem = 4u * (unsigned)desc->y_dim * (unsigned)(fbx * fby) * 8u;
+    for (int i = 0; i < 3; ++i) {
+      r = g_drv.moduleGetFunction(&p->fused[i], p->module, fnames[i]);
+      if (r == CUDA_SUCCESS && p->fsmem > 48 * 1024)
+        r = g_drv.funcSetAttribute(
+            p->fused[i], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+            (int)p->fsmem);
+      if (r != CUDA_SUCCESS) {
+        std::string m = std::string("fused kernel unavailable: ") + fnames[i] +
+                        ": " + cu_err(r);
+        pml_plan_destroy(p);
+        return fail(m);
+      }
+    }
+    auto cdivf = [](int a, int d) { return (unsigned)((a + d - 1) / d); };
+    p->fblock = dim3(fbx, fby, 1);
+    const int* n = desc->shape;
+    if (desc->n_dims == 3)
+      p->fgrid = dim3(cdivf(n[2], fbx - 2), cdivf(n[1], fby - 2),
+                      cdivf(n[0], desc->fused_zc));
+    else
+      p->fgrid = dim3(cdivf(n[1], fbx - 2), cdivf(n[0], desc->fused_zc), 1);
+  }
   r = g_drv.moduleGetFunction(&p->eval_rhs, p->module, "pml_eval_rhs");
   if (r != CUDA_SUCCESS) {
     pml_plan_destroy(p);
@@ -388,9 +427,38 @@ int pml_fdm_run(pml_plan* p, int integrator, const pml_workspace* ws,
       a.dir_slot = dir_slot;
       return launch(p, p->stage[k], params, s);
     };
+    auto fused = [&](int k, const double* u, double* u_out, double t_a,
+                     long long neu_a, long long dir_a, double t_b,
+                     long long neu_b, long long dir_b) {
+      PmlFusedArgs f;
+      a.u = u;
+      a.u_out = u_out;
+      a.acc_in = ws->acc;
+      a.acc_out = ws->acc;
+      a.t_eval = t_a;
+      a.neu_slot = neu_a;
+      a.dir_slot = dir_a;
+      f.s = a;
+      f.t_eval_b = t_b;
+      f.neu_slot_b = neu_b;
+      f.dir_slot_b = dir_b;
+      void* fparams[] = {&f};
+      CUresult r_ = g_drv.launchKernel(p->fused[k], p->fgrid.x, p->fgrid.y,
+                                       p->fgrid.z, p->fblock.x, p->fblock.y, 1,
+                                       p->fsmem, s, fparams, nullptr);
+      if (r_ != CUDA_SUCCESS) return fail("fused launch: " + cu_err(r_));
+      p->launches += 1;
+      return 0;
+    };
     int rc = 0;
     if (integrator == PML_INTEGRATOR_FORWARD_EULER) {
       rc = stage(0, y, nullptr, t, s_t, s_f);
+    } else if (p->desc.fused && integrator == PML_INTEGRATOR_EXPLICIT_MIDPOINT) {
+      rc = fused(2, y, nullptr, t, s_t, s_h, t + half, s_h, s_f);
+    } else if (p->desc.fused) {
+      // RK4: stages 1+2 write u_b (= u3) and acc; stages 3+4 write the slot
+      rc = fused(0, y, ws->u_b, t, s_t, s_h, t + half, s_h, s_h);
+      if (!rc) rc = fused(1, ws->u_b, nullptr, t + half, s_h, s_f, t + d_t, s_f, s_f);
     } else if (integrator == PML_INTEGRATOR_EXPLICIT_MIDPOINT) {
       rc = stage(1, y, ws->u_a, t, s_t, s_h);
       if (!rc) rc = stage(2, ws->u_a, nullptr, t + half, s_h, s_f);

@@ -86,6 +86,9 @@ class ProblemSpec:
     coherent_loads: bool = False
     eval_only: bool = False  # the differentiator entry points
     block: Optional[Tuple[int, int, int]] = None
+    #: (threads along the contiguous axis, threads along axis 1, planes per
+    #: chunk) of the fused stage-pair kernels, or None to generate none
+    fused: Optional[Tuple[int, int, int]] = None
 
 
 def default_block(shape) -> Tuple[int, int, int]:
@@ -96,6 +99,42 @@ def default_block(shape) -> Tuple[int, int, int]:
         return (128, 2, 1) if shape[1] >= 128 else (32, 8, 1)
     # measured on B200 (512^3 Burgers RK4): small row-shaped blocks win
     return (32, 4, 1) if shape[2] >= 32 else (16, 4, 4)
+
+
+N_SMS = 148
+
+
+def default_fused(shape, y_dim) -> Optional[Tuple[int, int, int]]:
+    """Tile of the fused stage-pair kernels (csrc/fdm_template.cuh): threads
+    cover the tile plus a one-cell halo ring; planes per chunk are chosen so
+    that the grid has several waves of thread blocks."""
+    if os.environ.get("PML_FUSE", "1") == "0":
+        return None
+    nd = len(shape)
+    if nd < 2 or any(n < 3 for n in shape):
+        return None
+    if os.environ.get("PML_FBLOCK"):
+        fbx, fby = (int(v) for v in os.environ["PML_FBLOCK"].split(","))
+    elif nd == 3:
+        fbx, fby = 32, 8
+    else:
+        fbx, fby = 128, 1
+    if nd == 2:
+        fby = 1
+    last = shape[-1]
+    fbx = max(32, min(fbx, 32 * -(-(last + 2) // 32)))
+    if 4 * y_dim * fbx * fby * 8 > 200 * 1024:
+        return None
+    tiles = -(-last // (fbx - 2))
+    if nd == 3:
+        tiles *= -(-shape[1] // (fby - 2))
+    if os.environ.get("PML_FZC"):
+        zc = int(os.environ["PML_FZC"])
+    else:
+        chunks = max(1, -(-(8 * N_SMS) // tiles))
+        zc = max(16, -(-shape[0] // chunks))
+    zc = min(zc, shape[0])
+    return (fbx, fby, zc)
 
 
 class _LeafBuilder:
@@ -117,23 +156,23 @@ class _LeafBuilder:
 
     # primitives ----------------------------------------------------------
     def Y(self, c):
-        return self._prim(f"Y{c}", f"PML_LD(P[{c}] + c.idx)")
+        return self._prim(f"Y{c}", f"S.at({c}, c.i0, c.i1, c.i2)")
 
     def D1(self, c, a):
         return self._prim(
             f"D1_{c}_{a}",
-            f"pml_d1_at<{a}, IM>(a, P[{c}], {c}, c.i0, c.i1, c.i2)",
+            f"pml_d1_at<{a}, IM>(a, S, {c}, c.i0, c.i1, c.i2)",
         )
 
     def D2(self, c, a, b=None):
         if b is None or a == b:
             return self._prim(
                 f"D2_{c}_{a}",
-                f"pml_d2_at<{a}, IM>(a, P[{c}], {c}, c.i0, c.i1, c.i2)",
+                f"pml_d2_at<{a}, IM>(a, S, {c}, c.i0, c.i1, c.i2)",
             )
         return self._prim(
             f"D2M_{c}_{a}_{b}",
-            f"pml_d2m_at<{a}, {b}, IM>(a, P[{c}], {c}, c.i0, c.i1, c.i2)",
+            f"pml_d2m_at<{a}, {b}, IM>(a, S, {c}, c.i0, c.i1, c.i2)",
         )
 
     def X(self, a):
@@ -379,10 +418,10 @@ def _emit_function(fn_name: str, spec: ProblemSpec, eq_indices: Sequence[int]):
     ]
     body = "\n".join(prim_lines + leaf_lines + out_lines)
     return (
-        "template <int IM>\n"
+        "template <int IM, class SRC>\n"
         f"__device__ __forceinline__ void {fn_name}(const PmlArgs& a, "
-        "const double* const* P, const PmlCell& c, double t, double* out) {\n"
-        "  (void)a; (void)P; (void)c; (void)t; (void)out;\n"
+        "const SRC& S, const PmlCell& c, double t, double* out) {\n"
+        "  (void)a; (void)S; (void)c; (void)t; (void)out;\n"
         f"{body}\n}}\n"
     )
 
@@ -417,6 +456,12 @@ def generate_source(spec: ProblemSpec) -> str:
     min_blocks = int(
         os.environ.get("PML_MIN_BLOCKS", str(max(1, 1024 // threads)))
     )
+    fused = spec.fused
+    if fused is not None:
+        fthreads = fused[0] * fused[1]
+        fmin = int(
+            os.environ.get("PML_FMIN_BLOCKS", str(max(1, 1024 // fthreads)))
+        )
     lines = [
         "// generated by pararealml_b200/operators/fdm/codegen.py",
         f"#define PML_NDIM {nd}",
@@ -434,6 +479,11 @@ def generate_source(spec: ProblemSpec) -> str:
         f"#define PML_NLAP {len(lap_idx)}",
         f"#define PML_STREAMING {int(os.environ.get('PML_STREAM', '0'))}",
         f"#define PML_MIN_BLOCKS {min_blocks}",
+        f"#define PML_FUSED {int(fused is not None)}",
+        f"#define PML_FBX {fused[0] if fused else 32}",
+        f"#define PML_FBY {fused[1] if fused else 1}",
+        f"#define PML_FZC {fused[2] if fused else 1}",
+        f"#define PML_FMIN_BLOCKS {fmin if fused else 1}",
         f"#define PML_BX {block[0]}",
         f"#define PML_BY {block[1]}",
         f"#define PML_BZ {block[2]}",

@@ -76,6 +76,12 @@ class DevicePlan:
         for i in range(3):
             desc.shape[i] = shape3[i]
             desc.block[i] = block[i]
+        fused = spec.fused
+        desc.fused = int(fused is not None)
+        if fused is not None:
+            desc.fused_block[0], desc.fused_block[1] = fused[0], fused[1]
+            desc.fused_zc = fused[2]
+        self.fused = fused
         desc.y_dim = low.y_dim
         desc.n_dt = len(low.kind_indices("D_Y_OVER_D_T"))
         desc.n_alg = len(low.kind_indices("Y"))

@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from pararealml_b200.operator import Operator, discretize_time_domain
+from pararealml_b200.operators.fdm import codegen
 from pararealml_b200.operators.fdm import device as dv
 from pararealml_b200.operators.fdm.lowering import (
     LoweredProblem,
@@ -70,7 +71,10 @@ def plan_overrides(cp, low: LoweredProblem, y0: Optional[np.ndarray]) -> dict:
         elif y0 is not None:
             probe = apply_dirichlet_host(cp, np.array(y0, copy=True), None)
             passthrough = bool(np.array_equal(probe, y0))
-    return {"passthrough": passthrough}
+    return {
+        "passthrough": passthrough,
+        "fused": codegen.default_fused(low.shape, low.y_dim),
+    }
 
 
 class FDMOperator(Operator):
