@@ -31,6 +31,12 @@ METRIC = "fp64 FDM cell-steps/s (3-D Burgers 512^3, RK4)"
 UNIT = "Gcell-steps/s"
 
 
+def metric_name(workload, n):
+    if workload == "burgers_3d" and n == 512:
+        return METRIC
+    return f"fp64 FDM cell-steps/s ({workload} {n}, RK4)"
+
+
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
@@ -253,15 +259,16 @@ class ClockSampler:
 # ---------------------------------------------------------------------------
 # CPU baseline (oracle port of the reference's NumPy path)
 # ---------------------------------------------------------------------------
-def cpu_baseline(n, n_steps):
+def cpu_baseline(workload, n, n_steps):
     import oracle
     import pararealml_b200 as ns
 
-    ivp, d_t = burgers_problem(ns, n, n_steps)
+    builder, _, _, dims, _ = WORKLOADS[workload]
+    ivp, d_t = builder(ns, n, n_steps)
     t0 = time.perf_counter()
     oracle.fdm_solve(ivp, "rk4", d_t)
     dt = time.perf_counter() - t0
-    return n**3 * n_steps / dt / 1e9, dt
+    return n**dims * n_steps / dt / 1e9, dt
 
 
 def peak_hbm():
@@ -430,17 +437,19 @@ def run_b200(args):
             }
             del sol
         cpu = None
-        if not args.no_cpu_baseline and args.workload == "burgers_3d":
-            v, secs = cpu_baseline(args.cpu_grid, 2)
+        if not args.no_cpu_baseline:
+            cpu_n = args.cpu_grid if dims == 3 else 8 * args.cpu_grid
+            v, secs = cpu_baseline(args.workload, cpu_n, 2)
             cpu = {
                 "value": v, "unit": UNIT, "cores": 1, "kind": "port",
                 "sample": f"oracle port of the reference NumPy RK4 FDM path, "
-                          f"3-D Burgers {args.cpu_grid}^3, 2 steps, {secs:.1f} s, "
-                          f"single process ({os.cpu_count()} host cores present)",
+                          f"{args.workload} on {'x'.join([str(cpu_n)] * dims)}, "
+                          f"2 steps, {secs:.1f} s, single process "
+                          f"({os.cpu_count()} host cores present)",
             }
         traffic = load_traffic().get(f"{args.workload}_{n}_rk4_step_dram_bytes")
         line = {
-            "metric": METRIC,
+            "metric": metric_name(args.workload, n),
             "value": value,
             "unit": UNIT,
             "n_gpus": 1,
@@ -529,7 +538,7 @@ def run_b200(args):
     if rank == 0:
         value = cells * total_steps * args.steps / (ms * 1e-3) / 1e9
         line = {
-            "metric": METRIC,
+            "metric": metric_name(args.workload, n),
             "value": value,
             "unit": UNIT,
             "n_gpus": world,

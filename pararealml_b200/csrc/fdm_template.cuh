@@ -123,111 +123,134 @@ __device__ __forceinline__ double pml_neu(const PmlArgs& a, int comp, int i0,
 }
 
 // ---------------------------------------------------------------------------
-// stencil sources: where the primitives read the field from
+// stencil sources: where the primitives read the field from.  A source returns
+// the value of a component at the cell c + (D0, D1, D2); the offsets are
+// compile-time constants so that every stencil load is a base pointer plus an
+// immediate.
 // ---------------------------------------------------------------------------
 // component planes in global memory
 struct PmlGlobalSrc {
   const double* const* P;
-  __device__ __forceinline__ double at(int comp, int i0, int i1, int i2) const {
-    return PML_LD(P[comp] + pml_lin(i0, i1, i2));
+  template <int D0, int D1, int D2>
+  __device__ __forceinline__ double rel(int comp, const PmlCell& c) const {
+    constexpr i64 off = D0 * PmlAx<0>::S + D1 * PmlAx<1>::S + D2 * PmlAx<2>::S;
+    return PML_LD(P[comp] + c.idx + off);
   }
 };
 
 // one plane (the Jacobi state of a single component)
 struct PmlPlaneSrc {
   const double* p;
-  __device__ __forceinline__ double at(int, int i0, int i1, int i2) const {
-    return PML_LD(p + pml_lin(i0, i1, i2));
+  template <int D0, int D1, int D2>
+  __device__ __forceinline__ double rel(int, const PmlCell& c) const {
+    constexpr i64 off = D0 * PmlAx<0>::S + D1 * PmlAx<1>::S + D2 * PmlAx<2>::S;
+    return PML_LD(p + c.idx + off);
   }
 };
 
-// first derivative along A at an arbitrary cell: zero ghost cells, boundary
-// planes overwritten by the Neumann value where one exists.
-// IM = interior mask: bit A set means the cell's coordinate along axis A is known
-// not to lie on a domain face, so the boundary handling of that axis compiles
-// away and its loads are unconditional
-template <int A, int IM, class SRC>
-__device__ __forceinline__ double pml_d1_at(const PmlArgs& a, const SRC& s,
-                                            int comp, int i0, int i1, int i2) {
+template <int A, int SIDE, int D0, int D1, int D2>
+__device__ __forceinline__ double pml_neu_rel(const PmlArgs& a, int comp,
+                                              const PmlCell& c) {
+  return pml_neu<A, SIDE>(a, comp, c.i0 + D0, c.i1 + D1, c.i2 + D2);
+}
+
+// first derivative along A at the cell c + D: zero ghost cells, boundary planes
+// overwritten by the Neumann value where one exists.
+// IM = interior mask: bit A set means the coordinate of c along axis A is known
+// not to lie on a domain face, so (for D_A == 0) the boundary handling of that
+// axis compiles away and its loads are unconditional
+template <int A, int IM, int D0, int D1, int D2, class SRC>
+__device__ __forceinline__ double pml_d1_rel(const PmlArgs& a, const SRC& s,
+                                             int comp, const PmlCell& c) {
   typedef PmlAx<A> X;
   constexpr int e0 = A == 0, e1 = A == 1, e2 = A == 2;
-  if ((IM >> A) & 1)
-    return (s.at(comp, i0 + e0, i1 + e1, i2 + e2) -
-            s.at(comp, i0 - e0, i1 - e1, i2 - e2)) * X::INV2H;
-  const int ia = pml_ia<A>(i0, i1, i2);
-  const double lo = ia > 0 ? s.at(comp, i0 - e0, i1 - e1, i2 - e2) : 0.0;
-  const double hi = ia < X::N - 1 ? s.at(comp, i0 + e0, i1 + e1, i2 + e2) : 0.0;
+  constexpr int da = A == 0 ? D0 : (A == 1 ? D1 : D2);
+  if (((IM >> A) & 1) && da == 0)
+    return (s.template rel<D0 + e0, D1 + e1, D2 + e2>(comp, c) -
+            s.template rel<D0 - e0, D1 - e1, D2 - e2>(comp, c)) * X::INV2H;
+  const int ia = pml_ia<A>(c.i0, c.i1, c.i2) + da;
+  const double lo =
+      ia > 0 ? s.template rel<D0 - e0, D1 - e1, D2 - e2>(comp, c) : 0.0;
+  const double hi = ia < X::N - 1
+                        ? s.template rel<D0 + e0, D1 + e1, D2 + e2>(comp, c)
+                        : 0.0;
   double d = (hi - lo) * X::INV2H;
   if (((PML_NEU_MASK >> (A * 2)) & 1) && ia == 0) {
-    const double g = pml_neu<A, 0>(a, comp, i0, i1, i2);
+    const double g = pml_neu_rel<A, 0, D0, D1, D2>(a, comp, c);
     if (g == g) d = g;
   }
   if (((PML_NEU_MASK >> (A * 2 + 1)) & 1) && ia == X::N - 1) {
-    const double g = pml_neu<A, 1>(a, comp, i0, i1, i2);
+    const double g = pml_neu_rel<A, 1, D0, D1, D2>(a, comp, c);
     if (g == g) d = g;
   }
   return d;
 }
 
-// neighbour pair with the second-difference ghost rule:
+template <int A, int IM, class SRC>
+__device__ __forceinline__ double pml_d1_at(const PmlArgs& a, const SRC& s,
+                                            int comp, const PmlCell& c) {
+  return pml_d1_rel<A, IM, 0, 0, 0>(a, s, comp, c);
+}
+
+// neighbour pair of c along A with the second-difference ghost rule:
 // ghost = inner neighbour -/+ 2 h g where a Neumann value g exists, else 0
 template <int A, int IM, class SRC>
 __device__ __forceinline__ void pml_nb2(const PmlArgs& a, const SRC& s, int comp,
-                                        int i0, int i1, int i2, double& lo,
+                                        const PmlCell& c, double& lo,
                                         double& hi) {
   typedef PmlAx<A> X;
   constexpr int e0 = A == 0, e1 = A == 1, e2 = A == 2;
   if ((IM >> A) & 1) {
-    lo = s.at(comp, i0 - e0, i1 - e1, i2 - e2);
-    hi = s.at(comp, i0 + e0, i1 + e1, i2 + e2);
+    lo = s.template rel<-e0, -e1, -e2>(comp, c);
+    hi = s.template rel<e0, e1, e2>(comp, c);
     return;
   }
-  const int ia = pml_ia<A>(i0, i1, i2);
+  const int ia = pml_ia<A>(c.i0, c.i1, c.i2);
   if (ia > 0) {
-    lo = s.at(comp, i0 - e0, i1 - e1, i2 - e2);
+    lo = s.template rel<-e0, -e1, -e2>(comp, c);
   } else {
     lo = 0.0;
     if ((PML_NEU_MASK >> (A * 2)) & 1) {
-      const double g = pml_neu<A, 0>(a, comp, i0, i1, i2);
-      if (g == g) lo = s.at(comp, i0 + e0, i1 + e1, i2 + e2) + (-2.0 * X::H) * g;
+      const double g = pml_neu<A, 0>(a, comp, c.i0, c.i1, c.i2);
+      if (g == g) lo = s.template rel<e0, e1, e2>(comp, c) + (-2.0 * X::H) * g;
     }
   }
   if (ia < X::N - 1) {
-    hi = s.at(comp, i0 + e0, i1 + e1, i2 + e2);
+    hi = s.template rel<e0, e1, e2>(comp, c);
   } else {
     hi = 0.0;
     if ((PML_NEU_MASK >> (A * 2 + 1)) & 1) {
-      const double g = pml_neu<A, 1>(a, comp, i0, i1, i2);
-      if (g == g) hi = s.at(comp, i0 - e0, i1 - e1, i2 - e2) + (2.0 * X::H) * g;
+      const double g = pml_neu<A, 1>(a, comp, c.i0, c.i1, c.i2);
+      if (g == g) hi = s.template rel<-e0, -e1, -e2>(comp, c) + (2.0 * X::H) * g;
     }
   }
 }
 
 template <int A, int IM, class SRC>
 __device__ __forceinline__ double pml_d2_at(const PmlArgs& a, const SRC& s,
-                                            int comp, int i0, int i1, int i2) {
+                                            int comp, const PmlCell& c) {
   double lo, hi;
-  pml_nb2<A, IM>(a, s, comp, i0, i1, i2, lo, hi);
-  const double c = s.at(comp, i0, i1, i2);
-  return ((hi - 2.0 * c) + lo) * PmlAx<A>::INVHH;
+  pml_nb2<A, IM>(a, s, comp, c, lo, hi);
+  const double v = s.template rel<0, 0, 0>(comp, c);
+  return ((hi - 2.0 * v) + lo) * PmlAx<A>::INVHH;
 }
 
 // mixed second derivative: constrained d/dA, then unconstrained zero-ghost d/dB
 template <int A, int B, int IM, class SRC>
 __device__ __forceinline__ double pml_d2m_at(const PmlArgs& a, const SRC& s,
-                                             int comp, int i0, int i1, int i2) {
+                                             int comp, const PmlCell& c) {
   typedef PmlAx<B> X;
-  const int ib = pml_ia<B>(i0, i1, i2);
+  const int ib = pml_ia<B>(c.i0, c.i1, c.i2);
   constexpr int e0 = B == 0, e1 = B == 1, e2 = B == 2;
-  // the two points i -/+ e_B keep the cell's coordinate along A, so the
-  // interior knowledge about axis A carries over to their d/dA
+  // the two points c -/+ e_B keep the coordinate of c along A, so the interior
+  // knowledge about axis A carries over to their d/dA
   constexpr bool b_in = (IM >> B) & 1;
-  const double lo =
-      (b_in || ib > 0)
-          ? pml_d1_at<A, IM>(a, s, comp, i0 - e0, i1 - e1, i2 - e2) : 0.0;
-  const double hi =
-      (b_in || ib < X::N - 1)
-          ? pml_d1_at<A, IM>(a, s, comp, i0 + e0, i1 + e1, i2 + e2) : 0.0;
+  const double lo = (b_in || ib > 0)
+                        ? pml_d1_rel<A, IM, -e0, -e1, -e2>(a, s, comp, c)
+                        : 0.0;
+  const double hi = (b_in || ib < X::N - 1)
+                        ? pml_d1_rel<A, IM, e0, e1, e2>(a, s, comp, c)
+                        : 0.0;
   return (hi - lo) * X::INV2H;
 }
 
@@ -490,19 +513,23 @@ struct PmlFusedArgs {
 #define PML_RPLANE (PML_FBX)
 #endif
 
-// stage-A results of the last four planes, in shared memory
+// stage-A results of the planes z - 1, z, z + 1 around the plane stage B works
+// on, in shared memory: base[d + 1] points at this thread's cell in the slot of
+// plane z + d, so a stencil read is base + immediate
 struct PmlRingSrc {
-  const double* ring;  // [4][C][PML_RPLANE]
-  const double* y;     // passthrough components are read from the state itself
-  int o1, o2;          // mesh coordinates of the ring's first in-plane cell
-  __device__ __forceinline__ double at(int comp, int i0, int i1, int i2) const {
-    if (PML_PASSTHROUGH && PML_KIND[comp] != 0)
-      return PML_LD(y + (i64)comp * PML_NCELLS + pml_lin(i0, i1, i2));
+  const double* base[3];
+  const double* y;  // passthrough components are read from the state itself
+  template <int D0, int D1, int D2>
+  __device__ __forceinline__ double rel(int comp, const PmlCell& c) const {
+    if (PML_PASSTHROUGH && PML_KIND[comp] != 0) {
+      constexpr i64 off =
+          D0 * PmlAx<0>::S + D1 * PmlAx<1>::S + D2 * PmlAx<2>::S;
+      return PML_LD(y + (i64)comp * PML_NCELLS + c.idx + off);
+    }
 #if PML_NDIM == 3
-    return ring[((i0 & 3) * PML_C + comp) * PML_RPLANE + (i1 - o1) * PML_FBX +
-                (i2 - o2)];
+    return base[D0 + 1][comp * PML_RPLANE + D1 * PML_FBX + D2];
 #else
-    return ring[((i0 & 3) * PML_C + comp) * PML_RPLANE + (i1 - o1)];
+    return base[D0 + 1][comp * PML_RPLANE + D1];
 #endif
   }
 };
@@ -548,7 +575,6 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
     P[k] = (from_y ? a.y : a.u) + (i64)k * PML_NCELLS;
   }
   const PmlGlobalSrc gsrc{P};
-  const PmlRingSrc rsrc{ring, a.y, o1, o2};
 
   constexpr int NK = PML_NDT > 0 ? PML_NDT : 1;
   double ka_prev[NK], y_prev[NK];
@@ -615,6 +641,12 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
       c.idx = pml_lin(zz, i1, i2);
       const int path = pml_warp_path(active, c);
       if (active) {
+        PmlRingSrc rsrc;
+        rsrc.y = a.y;
+#pragma unroll
+        for (int d = -1; d <= 1; ++d)
+          rsrc.base[d + 1] =
+              ring + (i64)(((zz + d) & 3) * PML_C) * PML_RPLANE + rcell;
         double K[NK];
         pml_eval_dt(path, b, rsrc, c, b.t_eval, K);
 #pragma unroll
@@ -727,14 +759,14 @@ extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ)
       const PmlPlaneSrc ps{p};
       double lo, hi, acc = 0.0;
 #if PML_COORD == 0
-      pml_nb2<0, 0>(a, ps, comp, c.i0, c.i1, c.i2, lo, hi);
+      pml_nb2<0, 0>(a, ps, comp, c, lo, hi);
       acc += (lo + hi) * PML_INVHH0;
 #if PML_NDIM >= 2
-      pml_nb2<1, 0>(a, ps, comp, c.i0, c.i1, c.i2, lo, hi);
+      pml_nb2<1, 0>(a, ps, comp, c, lo, hi);
       acc += (lo + hi) * PML_INVHH1;
 #endif
 #if PML_NDIM >= 3
-      pml_nb2<2, 0>(a, ps, comp, c.i0, c.i1, c.i2, lo, hi);
+      pml_nb2<2, 0>(a, ps, comp, c, lo, hi);
       acc += (lo + hi) * PML_INVHH2;
 #endif
       acc -= PML_LD(j.rhs + (i64)q * PML_NCELLS + c.idx);
@@ -743,25 +775,25 @@ extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ)
       const double r = __ldg(a.coord[0] + c.i0);
       const double r2 = r * r;
       double diag;
-      pml_nb2<0, 0>(a, ps, comp, c.i0, c.i1, c.i2, lo, hi);
+      pml_nb2<0, 0>(a, ps, comp, c, lo, hi);
 #if PML_COORD == 3
       const double s = __ldg(a.aux[1] + c.i2), co = __ldg(a.aux[2] + c.i2);
       const double r2s2 = r2 * (s * s);
       acc += (lo + hi) / (PML_H0 * PML_H0) + (hi - lo) / (PML_H0 * r);
-      pml_nb2<1, 0>(a, ps, comp, c.i0, c.i1, c.i2, lo, hi);
+      pml_nb2<1, 0>(a, ps, comp, c, lo, hi);
       acc += ((lo + hi) / (PML_H1 * PML_H1)) / r2s2;
-      pml_nb2<2, 0>(a, ps, comp, c.i0, c.i1, c.i2, lo, hi);
+      pml_nb2<2, 0>(a, ps, comp, c, lo, hi);
       acc += ((lo + hi) / (PML_H2 * PML_H2) +
               co * (hi - lo) / (2.0 * PML_H2 * s)) / r2;
       diag = 2.0 / (PML_H0 * PML_H0) + 2.0 / ((PML_H1 * PML_H1) * r2s2) +
              2.0 / ((PML_H2 * PML_H2) * r2);
 #else
       acc += (lo + hi) / (PML_H0 * PML_H0) + (hi - lo) / (2.0 * PML_H0 * r);
-      pml_nb2<1, 0>(a, ps, comp, c.i0, c.i1, c.i2, lo, hi);
+      pml_nb2<1, 0>(a, ps, comp, c, lo, hi);
       acc += ((lo + hi) / (PML_H1 * PML_H1)) / r2;
       diag = 2.0 / (PML_H0 * PML_H0) + 2.0 / ((PML_H1 * PML_H1) * r2);
 #if PML_COORD == 2
-      pml_nb2<2, 0>(a, ps, comp, c.i0, c.i1, c.i2, lo, hi);
+      pml_nb2<2, 0>(a, ps, comp, c, lo, hi);
       acc += (lo + hi) / (PML_H2 * PML_H2);
       diag += 2.0 / (PML_H2 * PML_H2);
 #endif

@@ -108,7 +108,9 @@ def default_fused(shape, y_dim) -> Optional[Tuple[int, int, int]]:
     """Tile of the fused stage-pair kernels (csrc/fdm_template.cuh): threads
     cover the tile plus a one-cell halo ring; planes per chunk are chosen so
     that the grid has several waves of thread blocks."""
-    if os.environ.get("PML_FUSE", "1") == "0":
+    # opt-in: on B200 the fused pair kernels are correct but (round 1) still
+    # slower than four unfused stage launches, see DESIGN.md section 3
+    if os.environ.get("PML_FUSE", "0") != "1":
         return None
     nd = len(shape)
     if nd < 2 or any(n < 3 for n in shape):
@@ -156,23 +158,23 @@ class _LeafBuilder:
 
     # primitives ----------------------------------------------------------
     def Y(self, c):
-        return self._prim(f"Y{c}", f"S.at({c}, c.i0, c.i1, c.i2)")
+        return self._prim(f"Y{c}", f"S.template rel<0, 0, 0>({c}, c)")
 
     def D1(self, c, a):
         return self._prim(
             f"D1_{c}_{a}",
-            f"pml_d1_at<{a}, IM>(a, S, {c}, c.i0, c.i1, c.i2)",
+            f"pml_d1_at<{a}, IM>(a, S, {c}, c)",
         )
 
     def D2(self, c, a, b=None):
         if b is None or a == b:
             return self._prim(
                 f"D2_{c}_{a}",
-                f"pml_d2_at<{a}, IM>(a, S, {c}, c.i0, c.i1, c.i2)",
+                f"pml_d2_at<{a}, IM>(a, S, {c}, c)",
             )
         return self._prim(
             f"D2M_{c}_{a}_{b}",
-            f"pml_d2m_at<{a}, {b}, IM>(a, S, {c}, c.i0, c.i1, c.i2)",
+            f"pml_d2m_at<{a}, {b}, IM>(a, S, {c}, c)",
         )
 
     def X(self, a):
