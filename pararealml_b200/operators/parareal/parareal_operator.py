@@ -283,9 +283,23 @@ class PararealOperator(Operator):
     # device path: both operators are FDMOperator, static boundary conditions
     # ------------------------------------------------------------------
     def _solve_on_device(self, ivp, world: _World) -> Solution:
+        t, gather = self.solve_on_device(ivp, world=world)
+        y = gather() if self._gather_trajectory else gather
+        return Solution(
+            ivp, t, y, vertex_oriented=True, d_t=self._f.d_t, copy=False
+        )
+
+    def solve_on_device(self, ivp, y0_planes=None, world=None):
+        """The Parareal iteration with every state resident in HBM.  Leaves
+        this rank's (shifted) fine slice in ``last_slice_trajectory`` and
+        returns ``(t, gather)`` where ``gather()`` collects the full
+        trajectory on the host of every rank.  ``y0_planes`` may hold the
+        already uploaded initial state (component planes)."""
         from pararealml_b200.operators.fdm import device as dv
         from pararealml_b200.operators.fdm.fdm_operator import lowered
 
+        if world is None:
+            world = _World()
         f, g = self._f, self._g
         cp = ivp.constrained_problem
         t0, t1 = ivp.t_interval
@@ -301,9 +315,16 @@ class PararealOperator(Operator):
 
         # initial state with the static Dirichlet values re-applied, as the
         # DiscreteInitialCondition of every sub-IVP does (reference :159-161)
-        y0 = DiscreteInitialCondition(
-            cp, ivp.initial_condition.discrete_y_0(True), True
-        ).discrete_y_0(True)
+        # (a caller-provided ``y0_planes`` must already satisfy them)
+        y0 = None
+        if y0_planes is None:
+            ic = ivp.initial_condition
+            view = getattr(ic, "discrete_y_0_view", None)
+            y0 = view(True) if view is not None else None
+            if y0 is None:
+                y0 = ic.discrete_y_0(True)
+            if low.dir_mask != 0:
+                y0 = DiscreteInitialCondition(cp, y0, True).discrete_y_0(True)
         f_plan = f._plan_for(cp, low, y0)
         g_plan = g._plan_for(cp, low, y0)
 
@@ -311,7 +332,10 @@ class PararealOperator(Operator):
         # run slice by slice so that only one slice of it is resident
         t_g = discretize_time_domain(ivp.t_interval, g.d_t)
         ends = np.rint((borders[1:] - t0) / g.d_t).astype(int) - 1
-        u_start = dv.upload_state(y0, n_cells, y_dim)
+        u_start = (
+            y0_planes if y0_planes is not None
+            else dv.upload_state(y0, n_cells, y_dim)
+        )
         g_end = torch.empty(state, **f64)
         prev = u_start
         first = 0
@@ -402,5 +426,4 @@ class PararealOperator(Operator):
             torch.cuda.current_stream().synchronize()
             return host.numpy().reshape((len(t),) + tuple(y_shape))
 
-        y = gather() if self._gather_trajectory else gather
-        return Solution(ivp, t, y, vertex_oriented=True, d_t=f.d_t, copy=False)
+        return t, gather

@@ -35,17 +35,30 @@ def _entry(rank, world_size, port, backend, fn, args, errors):
             dist.destroy_process_group()
 
 
-def run_distributed(fn, world_size, args=(), backend="gloo"):
+def run_distributed(fn, world_size, args=(), backend="gloo", attempts=2):
+    """Runs ``fn(rank, world_size, *args)`` on ``world_size`` processes.  A
+    rendezvous failure (port stolen between probing and binding) is retried
+    once on a fresh port; assertion failures of ``fn`` are not."""
     ctx = mp.get_context("spawn")
-    errors = ctx.SimpleQueue()
-    port = free_port()
-    try:
-        mp.spawn(
-            _entry, args=(world_size, port, backend, fn, args, errors),
-            nprocs=world_size, join=True,
-        )
-    except Exception as e:
-        msgs = []
-        while not errors.empty():
-            msgs.append("rank %d:\n%s" % errors.get())
-        raise AssertionError("\n".join(msgs) or str(e))
+    for attempt in range(attempts):
+        errors = ctx.SimpleQueue()
+        port = free_port()
+        try:
+            mp.spawn(
+                _entry, args=(world_size, port, backend, fn, args, errors),
+                nprocs=world_size, join=True,
+            )
+            return
+        except Exception as e:
+            msgs = []
+            while not errors.empty():
+                msgs.append("rank %d:\n%s" % errors.get())
+            text = "\n".join(msgs) or str(e)
+            rendezvous = "AssertionError" not in text and (
+                "address already in use" in text.lower()
+                or "connect" in text.lower()
+                or not msgs
+            )
+            if rendezvous and attempt + 1 < attempts:
+                continue
+            raise AssertionError(text)
