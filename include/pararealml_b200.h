@@ -30,6 +30,7 @@ typedef struct pml_plan_desc {
   int fused;        /* 1: the source has the fused stage-pair kernels */
   int fused_block[2]; /* their thread block (contiguous axis, axis 1) */
   int fused_zc;     /* planes of the marching axis per thread block */
+  int small_threads; /* > 0: the source has the single-block time loop kernel */
 } pml_plan_desc;
 
 /* NaN-coded boundary tables and 1-D coordinate vectors (device pointers).
@@ -54,6 +55,8 @@ typedef struct pml_workspace {
   double* jac_b;     /* n_lap * n_cells */
   double* partials;  /* one double per thread block */
   int* flags;        /* 2 ints: done, sweeps */
+  double* t_dev;     /* step start times for the single-block kernel */
+  long long t_capacity; /* doubles available at t_dev */
 } pml_workspace;
 
 const char* pml_last_error(void);

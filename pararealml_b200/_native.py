@@ -34,6 +34,7 @@ class PlanDesc(Structure):
         ("fused", c_int),
         ("fused_block", c_int * 2),
         ("fused_zc", c_int),
+        ("small_threads", c_int),
     ]
 
 
@@ -58,6 +59,8 @@ class Workspace(Structure):
         ("jac_b", c_void_p),
         ("partials", c_void_p),
         ("flags", c_void_p),
+        ("t_dev", c_void_p),
+        ("t_capacity", c_longlong),
     ]
 
 

@@ -96,9 +96,10 @@ template <int A> __device__ __forceinline__ i64 pml_face(int i0, int i1, int i2)
 }
 
 #if PML_COHERENT_LOADS
-// single-CTA time loop: data written earlier in the same launch is re-read
-#define PML_LD(p) (*(const volatile double*)(p))
-#define PML_LD_ONCE(p) (*(const volatile double*)(p))
+// single-CTA time loop: data written earlier in the same launch is re-read, so
+// loads bypass the (non-coherent) L1 and read-only paths
+#define PML_LD(p) __ldcg(p)
+#define PML_LD_ONCE(p) __ldcg(p)
 #define PML_ST(p, v) (*(p) = (v))
 #else
 #define PML_LD(p) __ldg(p)
@@ -701,6 +702,85 @@ PML_FUSED_KERNEL(pml_fused_rk4_12, PML_F_RK4_12)
 PML_FUSED_KERNEL(pml_fused_rk4_34, PML_F_RK4_34)
 PML_FUSED_KERNEL(pml_fused_mid, PML_F_MID)
 #endif  // PML_FUSED
+
+// ---------------------------------------------------------------------------
+// Small meshes (and ODE systems): the whole time loop in ONE thread block.
+// Kernel launches cost more than a stage on a few thousand cells, so all steps
+// and stages run inside a single launch with __syncthreads() between stages
+// (same per-cell stage arithmetic as the multi-block kernels).
+// ---------------------------------------------------------------------------
+#if PML_SMALL
+struct PmlSmallArgs {
+  PmlArgs s;        // tables, d_t; s.y = state before the first step
+  double* traj;     // trajectory slots
+  i64 stride;
+  const double* t;  // start time of every step (device)
+  int n_steps;
+  int integrator;   // 0 forward Euler, 1 explicit midpoint, 2 RK4
+  i64 slot0;
+  double* u_a;
+  double* u_b;
+  double* acc;
+};
+
+template <int STAGE>
+__device__ __forceinline__ void pml_small_stage(const PmlArgs& a) {
+  for (int base = 0; base < (int)PML_NCELLS; base += PML_SMALL_THREADS) {
+    const int cell = base + (int)threadIdx.x;
+    PmlCell c;
+    c.idx = cell;
+    c.i0 = cell / (PML_N1 * PML_N2);
+    c.i1 = (cell / PML_N2) % PML_N1;
+    c.i2 = cell % PML_N2;
+    pml_stage_cell<STAGE>(a, cell < (int)PML_NCELLS, c);
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void pml_small_set(PmlArgs& a, const double* u,
+                                              double* u_out, double t_eval,
+                                              i64 neu_slot, i64 dir_slot) {
+  a.u = u;
+  a.u_out = u_out;
+  a.t_eval = t_eval;
+  a.neu_slot = neu_slot;
+  a.dir_slot = dir_slot;
+}
+
+extern "C" __global__ void __launch_bounds__(PML_SMALL_THREADS)
+    pml_small_run(const __grid_constant__ PmlSmallArgs f) {
+  PmlArgs a = f.s;
+  a.acc_in = f.acc;
+  a.acc_out = f.acc;
+  const double dt = a.dt, half = a.dt / 2.0;
+  for (int j = 0; j < f.n_steps; ++j) {
+    const double t = __ldg(f.t + j);
+    const double* y = j == 0 ? f.s.y : f.traj + (i64)(j - 1) * f.stride;
+    a.y = y;
+    a.y_next = f.traj + (i64)j * f.stride;
+    const i64 s_t = f.slot0 + 3 * (i64)j, s_h = s_t + 1, s_f = s_t + 2;
+    a.dir_slot_full = s_f;
+    if (f.integrator == 0) {
+      pml_small_set(a, y, nullptr, t, s_t, s_f);
+      pml_small_stage<PML_FE>(a);
+    } else if (f.integrator == 1) {
+      pml_small_set(a, y, f.u_a, t, s_t, s_h);
+      pml_small_stage<PML_MID1>(a);
+      pml_small_set(a, f.u_a, nullptr, t + half, s_h, s_f);
+      pml_small_stage<PML_MID2>(a);
+    } else {
+      pml_small_set(a, y, f.u_a, t, s_t, s_h);
+      pml_small_stage<PML_RK4_1>(a);
+      pml_small_set(a, f.u_a, f.u_b, t + half, s_h, s_h);
+      pml_small_stage<PML_RK4_2>(a);
+      pml_small_set(a, f.u_b, f.u_a, t + half, s_h, s_f);
+      pml_small_stage<PML_RK4_3>(a);
+      pml_small_set(a, f.u_a, nullptr, t + dt, s_f, s_f);
+      pml_small_stage<PML_RK4_4>(a);
+    }
+  }
+}
+#endif  // PML_SMALL
 
 // raw right-hand side evaluation (the NumPy-in / NumPy-out differentiator entry
 // points gradient/hessian/divergence/curl/laplacian are served by this kernel)

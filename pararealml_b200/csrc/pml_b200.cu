@@ -118,6 +118,19 @@ struct PmlFusedArgs {
   long long dir_slot_b;
 };
 
+struct PmlSmallArgs {
+  PmlArgs s;
+  double* traj;
+  long long stride;
+  const double* t;
+  int n_steps;
+  int integrator;
+  long long slot0;
+  double* u_a;
+  double* u_b;
+  double* acc;
+};
+
 struct PmlJacobiArgs {
   PmlArgs base;
   const double* y_hat;
@@ -180,6 +193,7 @@ struct pml_plan {
   CUfunction fused[3] = {};  // rk4 1+2, rk4 3+4, midpoint 1+2
   dim3 fgrid, fblock;
   unsigned fsmem = 0;
+  CUfunction small_run = nullptr;
   CUfunction eval_rhs = nullptr;
   CUfunction jac_init = nullptr, jac_sweep = nullptr, jac_check = nullptr,
              jac_store = nullptr;
@@ -341,6 +355,13 @@ int pml_plan_create(const char* source, const pml_plan_desc* desc,
     else
       p->fgrid = dim3(cdivf(n[1], fbx - 2), cdivf(n[0], desc->fused_zc), 1);
   }
+  if (desc->small_threads > 0) {
+    r = g_drv.moduleGetFunction(&p->small_run, p->module, "pml_small_run");
+    if (r != CUDA_SUCCESS) {
+      pml_plan_destroy(p);
+      return fail("missing kernel pml_small_run");
+    }
+  }
   r = g_drv.moduleGetFunction(&p->eval_rhs, p->module, "pml_eval_rhs");
   if (r != CUDA_SUCCESS) {
     pml_plan_destroy(p);
@@ -407,6 +428,35 @@ int pml_fdm_run(pml_plan* p, int integrator, const pml_workspace* ws,
   a.lap_rhs = ws->lap_rhs;
   const double half = d_t / 2.0;
   const long long lap_elems = (long long)p->desc.n_lap * p->n_cells;
+  if (p->small_run && p->desc.n_lap == 0 && ws->t_dev && ws->t_capacity > 0) {
+    // small mesh: all steps of a chunk in one single-block launch
+    for (int first = 0; first < n_steps; first += (int)ws->t_capacity) {
+      const int count = n_steps - first < ws->t_capacity
+                            ? n_steps - first : (int)ws->t_capacity;
+      PML_CUDA(cudaMemcpyAsync(ws->t_dev, t_host + first, count * sizeof(double),
+                               cudaMemcpyHostToDevice, (cudaStream_t)s));
+      PmlSmallArgs f;
+      f.s = a;
+      f.s.y = first == 0 ? y0 : traj + (long long)(first - 1) * stride;
+      f.traj = traj + (long long)first * stride;
+      f.stride = stride;
+      f.t = ws->t_dev;
+      f.n_steps = count;
+      f.integrator = integrator;
+      f.slot0 = slot0 + 3LL * first;
+      f.u_a = ws->u_a;
+      f.u_b = ws->u_b;
+      f.acc = ws->acc;
+      void* sparams[] = {&f};
+      PML_CU(g_drv.launchKernel(p->small_run, 1, 1, 1,
+                                (unsigned)p->desc.small_threads, 1, 1, 0, s,
+                                sparams, nullptr));
+      p->launches += 1;
+      // t_host may be reused by the caller and t_dev by the next chunk
+      PML_CUDA(cudaStreamSynchronize((cudaStream_t)s));
+    }
+    return 0;
+  }
   for (int j = 0; j < n_steps; ++j) {
     const double t = t_host[j];
     const double* y = j == 0 ? y0 : traj + (long long)(j - 1) * stride;

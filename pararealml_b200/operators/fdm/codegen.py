@@ -89,6 +89,8 @@ class ProblemSpec:
     #: (threads along the contiguous axis, threads along axis 1, planes per
     #: chunk) of the fused stage-pair kernels, or None to generate none
     fused: Optional[Tuple[int, int, int]] = None
+    #: threads of the single-block time-loop kernel for small meshes (0: none)
+    small_threads: int = 0
 
 
 def default_block(shape) -> Tuple[int, int, int]:
@@ -102,6 +104,18 @@ def default_block(shape) -> Tuple[int, int, int]:
 
 
 N_SMS = 148
+SMALL_MESH_CELLS = 8192
+
+
+def default_small(shape) -> int:
+    """Meshes of at most SMALL_MESH_CELLS cells (and ODE systems) run their
+    whole time loop in one thread block."""
+    if os.environ.get("PML_SMALL", "1") == "0":
+        return 0
+    cells = int(np.prod(shape)) if len(shape) else 1
+    if cells > SMALL_MESH_CELLS:
+        return 0
+    return int(min(1024, max(32, 32 * -(-cells // 32))))
 
 
 def default_fused(shape, y_dim) -> Optional[Tuple[int, int, int]]:
@@ -475,7 +489,9 @@ def generate_source(spec: ProblemSpec) -> str:
         f"#define PML_NEU_MASK {spec.neu_mask}",
         f"#define PML_DIR_MASK {spec.dir_mask}",
         f"#define PML_PASSTHROUGH {int(spec.passthrough)}",
-        f"#define PML_COHERENT_LOADS {int(spec.coherent_loads)}",
+        f"#define PML_COHERENT_LOADS {int(spec.coherent_loads or spec.small_threads > 0)}",
+        f"#define PML_SMALL {int(spec.small_threads > 0)}",
+        f"#define PML_SMALL_THREADS {max(spec.small_threads, 32)}",
         f"#define PML_NDT {len(dt_idx)}",
         f"#define PML_NALG {len(alg_idx)}",
         f"#define PML_NLAP {len(lap_idx)}",

@@ -82,6 +82,7 @@ class DevicePlan:
             desc.fused_block[0], desc.fused_block[1] = fused[0], fused[1]
             desc.fused_zc = fused[2]
         self.fused = fused
+        desc.small_threads = int(spec.small_threads)
         desc.y_dim = low.y_dim
         desc.n_dt = len(low.kind_indices("D_Y_OVER_D_T"))
         desc.n_alg = len(low.kind_indices("Y"))
@@ -135,9 +136,12 @@ class DevicePlan:
             nl = max(self.n_lap, 0) * self.n_cells
             for k in ("lap_rhs", "jac_a", "jac_b"):
                 bufs[k] = torch.empty(max(nl, 1), **f64)
+            t_capacity = 4096 if self.spec.small_threads else 0
+            bufs["t_dev"] = torch.empty(max(t_capacity, 1), **f64)
             ws = _native.Workspace()
             for k, t in bufs.items():
                 setattr(ws, k, t.data_ptr())
+            ws.t_capacity = t_capacity
             self._ws_bufs = bufs
             self._ws = ws
         return self._ws

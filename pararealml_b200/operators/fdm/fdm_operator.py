@@ -74,6 +74,7 @@ def plan_overrides(cp, low: LoweredProblem, y0: Optional[np.ndarray]) -> dict:
     return {
         "passthrough": passthrough,
         "fused": codegen.default_fused(low.shape, low.y_dim),
+        "small_threads": codegen.default_small(low.shape),
     }
 
 

@@ -35,9 +35,9 @@ def test_library_exports_every_symbol_of_the_header():
 
 
 def test_struct_layouts_match_the_header():
-    assert ctypes.sizeof(_native.PlanDesc) == 4 * 15
+    assert ctypes.sizeof(_native.PlanDesc) == 4 * 16
     assert ctypes.sizeof(_native.Tables) == 8 * (6 * 4 + 3 + 4)
-    assert ctypes.sizeof(_native.Workspace) == 8 * 8
+    assert ctypes.sizeof(_native.Workspace) == 8 * 10
 
 
 @pytest.mark.parametrize("case", cases.FDM_CASES, ids=lambda c: c.name)
