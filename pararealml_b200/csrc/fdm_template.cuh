@@ -508,15 +508,26 @@ struct PmlFusedArgs {
   i64 dir_slot_b;
 };
 
+// in-plane extent of the thread layout (= stage-A cells = tile + halo 1) and of
+// the input ring (tile + halo 2)
 #if PML_NDIM == 3
-#define PML_RPLANE (PML_FBX * PML_FBY)
+#define PML_MID_PITCH PML_FBX
+#define PML_MID_PLANE (PML_FBX * PML_FBY)
+#define PML_IN_PITCH (PML_FBX + 2)
+#define PML_IN_PLANE ((PML_FBX + 2) * (PML_FBY + 2))
 #else
-#define PML_RPLANE (PML_FBX)
+#define PML_MID_PITCH 0
+#define PML_MID_PLANE (PML_FBX)
+#define PML_IN_PITCH 0
+#define PML_IN_PLANE (PML_FBX + 2)
 #endif
+#define PML_IN_EXTRA (PML_IN_PLANE - PML_MID_PLANE)
+#define PML_F_THREADS (PML_FBX * PML_FBY)
+#define PML_RING_DOUBLES (4 * PML_C * (PML_IN_PLANE + PML_MID_PLANE))
 
-// stage-A results of the planes z - 1, z, z + 1 around the plane stage B works
-// on, in shared memory: base[d + 1] points at this thread's cell in the slot of
-// plane z + d, so a stencil read is base + immediate
+// a 4-slot ring of planes in shared memory: base[d + 1] points at this thread's
+// cell in the slot of plane z + d, so a stencil read is base + immediate
+template <int PITCH, int PLANE>
 struct PmlRingSrc {
   const double* base[3];
   const double* y;  // passthrough components are read from the state itself
@@ -528,67 +539,145 @@ struct PmlRingSrc {
       return PML_LD(y + (i64)comp * PML_NCELLS + c.idx + off);
     }
 #if PML_NDIM == 3
-    return base[D0 + 1][comp * PML_RPLANE + D1 * PML_FBX + D2];
+    return base[D0 + 1][comp * PLANE + D1 * PITCH + D2];
 #else
-    return base[D0 + 1][comp * PML_RPLANE + D1];
+    return base[D0 + 1][comp * PLANE + D1];
 #endif
   }
 };
 
 enum { PML_F_RK4_12 = 0, PML_F_RK4_34 = 1, PML_F_MID = 2 };
 
+// Dataflow of one thread block (marching index z, ONE barrier per plane):
+//   iteration z:  input plane z+1 (prefetched into registers one iteration
+//                 earlier) -> in_ring slot (z+1)&3; prefetch plane z+2;
+//                 barrier;
+//                 stage A on plane z   (reads in_ring z-1..z+1, writes mid_ring z)
+//                 stage B on plane z-2 (reads mid_ring z-3..z-1, writes HBM)
+// The slot written in an iteration is never one a lagging warp may still read:
+// in_ring (z+1)&3 == (z-3)&3 vs. stage A(z-1) reading z-2..z; mid_ring z&3 ==
+// (z-4)&3 vs. stage B(z-3) reading z-4..z-2 happens before the barrier.
 template <int MODE>
 __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
-                                               double* ring) {
+                                               double* smem) {
   const PmlArgs& a = f.s;
-  constexpr bool first = MODE != PML_F_RK4_34;  // stage A reads y itself
+  constexpr bool first = MODE != PML_F_RK4_34;  // stage A's input is y itself
+  double* in_ring = smem;
+  double* mid_ring = smem + 4 * PML_C * PML_IN_PLANE;
   const int tx = threadIdx.x;
 #if PML_NDIM == 3
   const int ty = threadIdx.y;
-  const int o2 = blockIdx.x * (PML_FBX - 2) - 1;
+  const int tid = ty * PML_FBX + tx;
+  const int o2 = blockIdx.x * (PML_FBX - 2) - 1;  // mesh coords of thread (0,0)
   const int o1 = blockIdx.y * (PML_FBY - 2) - 1;
   const int i2 = o2 + tx, i1 = o1 + ty;
   const bool in_plane = i1 >= 0 && i1 < PML_N1 && i2 >= 0 && i2 < PML_N2;
   const bool owner = in_plane && tx >= 1 && tx <= PML_FBX - 2 && ty >= 1 &&
                      ty <= PML_FBY - 2;
-  const int rcell = ty * PML_FBX + tx;
+  const int mid_cell = ty * PML_MID_PITCH + tx;
+  const int in_cell = (ty + 1) * PML_IN_PITCH + (tx + 1);
   const int chunk = blockIdx.z;
+  // the halo ring of the input tile is loaded by the first PML_IN_EXTRA threads
+  int e1 = 0, e2 = 0;  // in-ring coordinates of this thread's extra cell
+  {
+    const int t = tid;
+    const int row = PML_FBX + 2;
+    if (t < row) { e1 = 0; e2 = t; }
+    else if (t < 2 * row) { e1 = PML_FBY + 1; e2 = t - row; }
+    else if (t < 2 * row + PML_FBY) { e1 = t - 2 * row + 1; e2 = 0; }
+    else { e1 = t - 2 * row - PML_FBY + 1; e2 = PML_FBX + 1; }
+  }
+  const int x1 = o1 - 1 + e1, x2 = o2 - 1 + e2;  // mesh coords of the extra cell
+  const bool extra = tid < PML_IN_EXTRA && x1 >= 0 && x1 < PML_N1 && x2 >= 0 &&
+                     x2 < PML_N2;
+  const int extra_cell = e1 * PML_IN_PITCH + e2;
 #else
-  const int o1 = blockIdx.x * (PML_FBX - 2) - 1, o2 = 0;
+  const int tid = tx;
+  const int o1 = blockIdx.x * (PML_FBX - 2) - 1;
   const int i1 = o1 + tx, i2 = 0;
   const bool in_plane = i1 >= 0 && i1 < PML_N1;
   const bool owner = in_plane && tx >= 1 && tx <= PML_FBX - 2;
-  const int rcell = tx;
+  const int mid_cell = tx;
+  const int in_cell = tx + 1;
   const int chunk = blockIdx.y;
+  const int e1 = tid == 0 ? 0 : PML_FBX + 1;
+  const int x1 = o1 - 1 + e1, x2 = 0;
+  const bool extra = tid < 2 && x1 >= 0 && x1 < PML_N1;
+  const int extra_cell = e1;
 #endif
   const int z_begin = chunk * PML_FZC;
   const int z_end = min(z_begin + PML_FZC, PML_N0);
+  // planes: stage B works on [z_begin, z_end), stage A on one more plane on
+  // each side, the input ring on two more
+  const int za_lo = max(z_begin - 1, 0), za_hi = min(z_end, PML_N0 - 1);
+  const int zi_lo = max(z_begin - 2, 0), zi_hi = min(z_end + 1, PML_N0 - 1);
 
   PmlArgs b = a;  // stage B sees its own time and table slots
   b.t_eval = f.t_eval_b;
   b.neu_slot = f.neu_slot_b;
   b.dir_slot = f.dir_slot_b;
 
-  const double* P[PML_C];
+  // stage A's stencil input: y (first stages) or the previous stage's output
+  const double* IN[PML_C];
 #pragma unroll
-  for (int k = 0; k < PML_C; ++k) {
-    const bool from_y = first || (PML_PASSTHROUGH && PML_KIND[k] != 0);
-    P[k] = (from_y ? a.y : a.u) + (i64)k * PML_NCELLS;
-  }
-  const PmlGlobalSrc gsrc{P};
+  for (int k = 0; k < PML_C; ++k)
+    IN[k] = ((first || (PML_PASSTHROUGH && PML_KIND[k] != 0)) ? a.y : a.u) +
+            (i64)k * PML_NCELLS;
+  const i64 own_off = pml_lin(0, in_plane ? i1 : 0, in_plane ? i2 : 0);
+  const i64 extra_off = pml_lin(0, extra ? x1 : 0, extra ? x2 : 0);
 
   constexpr int NK = PML_NDT > 0 ? PML_NDT : 1;
-  double ka_prev[NK], y_prev[NK];
+  // prefetch registers: input plane (own + extra cell), step-start state
+  double pre_own[PML_C], pre_extra[PML_C], pre_y[NK];
+  auto prefetch = [&](int zp) {
+    const bool valid = zp >= zi_lo && zp <= zi_hi;
+    const i64 zoff = (i64)zp * PmlAx<0>::S;
 #pragma unroll
-  for (int j = 0; j < NK; ++j) ka_prev[j] = y_prev[j] = 0.0;
+    for (int k = 0; k < PML_C; ++k) {
+      const bool ring_comp = !(PML_PASSTHROUGH && PML_KIND[k] != 0);
+      pre_own[k] = (ring_comp && valid && in_plane)
+                       ? PML_LD(IN[k] + zoff + own_off) : 0.0;
+      pre_extra[k] = (ring_comp && valid && extra)
+                         ? PML_LD(IN[k] + zoff + extra_off) : 0.0;
+    }
+  };
+  auto deposit = [&](int zp) {
+    double* slot = in_ring + (i64)((zp & 3) * PML_C) * PML_IN_PLANE;
+#pragma unroll
+    for (int k = 0; k < PML_C; ++k) {
+      if (PML_PASSTHROUGH && PML_KIND[k] != 0) continue;
+      slot[k * PML_IN_PLANE + in_cell] = pre_own[k];
+      if (tid < PML_IN_EXTRA) slot[k * PML_IN_PLANE + extra_cell] = pre_extra[k];
+    }
+  };
 
-  for (int z = max(z_begin - 1, 0); z <= z_end; ++z) {
-    // ---- stage A on plane z (halo'd tile) --------------------------------
+  // results of stage A that stage B needs two planes later
+  double ka_1[NK], y_1[NK], ka_2[NK], y_2[NK];
+#pragma unroll
+  for (int j = 0; j < NK; ++j) ka_1[j] = y_1[j] = ka_2[j] = y_2[j] = pre_y[j] = 0.0;
+
+  // prologue: planes zi_lo .. za_lo into the ring, za_lo + 1 into registers
+  for (int zp = zi_lo; zp <= za_lo; ++zp) {
+    prefetch(zp);
+    deposit(zp);
+  }
+  prefetch(za_lo + 1);
+
+  for (int z = za_lo; z <= z_end + 1; ++z) {
+    deposit(z + 1);       // plane z + 1 was prefetched during the last iteration
+    prefetch(z + 2);      // consumed in the next iteration
+    if (!first) {
+      // step-start state at the stage-A cell of the NEXT iteration's plane is
+      // not needed early: it is read below together with the ring (cheap,
+      // coalesced, L2 resident after stage 1+2 of the same step)
+    }
+    __syncthreads();
+    // ---- stage A on plane z (halo'd tile), stencil reads from the input ring
     double ka_new[NK], y_new[NK];
 #pragma unroll
     for (int j = 0; j < NK; ++j) ka_new[j] = y_new[j] = 0.0;
     {
-      const bool active = in_plane && z < PML_N0;
+      const bool active = in_plane && z >= za_lo && z <= za_hi;
       PmlCell c;
       c.i0 = z;
       c.i1 = i1;
@@ -596,44 +685,49 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
       c.idx = pml_lin(z, i1, i2);
       const int path = pml_warp_path(active, c);
       if (active) {
+        PmlRingSrc<PML_IN_PITCH, PML_IN_PLANE> src;
+        src.y = a.y;
+#pragma unroll
+        for (int d = -1; d <= 1; ++d)
+          src.base[d + 1] =
+              in_ring + (i64)(((z + d) & 3) * PML_C) * PML_IN_PLANE + in_cell;
         double K[NK];
-        pml_eval_dt(path, a, gsrc, c, a.t_eval, K);
-        double* slot = ring + (i64)((z & 3) * PML_C) * PML_RPLANE + rcell;
+        pml_eval_dt(path, a, src, c, a.t_eval, K);
+        double* slot = mid_ring + (i64)((z & 3) * PML_C) * PML_MID_PLANE + mid_cell;
 #pragma unroll
         for (int j = 0; j < PML_NDT; ++j) {
           const int k = PML_DT_IDX[j];
           const i64 o = (i64)k * PML_NCELLS + c.idx;
-          const double y0 = first ? PML_LD(P[k] + c.idx) : PML_LD(a.y + o);
+          const double y0 = first ? src.template rel<0, 0, 0>(k, c)
+                                  : PML_LD(a.y + o);
           double ua;
           if (MODE == PML_F_MID) {
             ua = y0 + (a.dt / 2.0) * K[j];
-            ka_new[j] = 0.0;
           } else {
             const double kk = a.dt * K[j];
             ua = MODE == PML_F_RK4_12 ? y0 + kk / 2.0 : y0 + kk;
             ka_new[j] = kk;
           }
           y_new[j] = y0;
-          slot[k * PML_RPLANE] = pml_dirichlet(a, a.dir_slot, k, c, ua);
+          slot[k * PML_MID_PLANE] = pml_dirichlet(a, a.dir_slot, k, c, ua);
         }
 #if PML_NALG + PML_NLAP > 0
         if (!PML_PASSTHROUGH) {
 #pragma unroll
           for (int k = 0; k < PML_C; ++k) {
             if (PML_KIND[k] == 0) continue;
-            slot[k * PML_RPLANE] = pml_dirichlet(
+            slot[k * PML_MID_PLANE] = pml_dirichlet(
                 a, a.dir_slot, k, c, PML_LD(a.y + (i64)k * PML_NCELLS + c.idx));
           }
         }
         if (first && owner && z >= z_begin && z < z_end)
-          pml_first_stage_extras(path, a, gsrc, c);
+          pml_first_stage_extras(path, a, src, c);
 #endif
       }
     }
-    __syncthreads();
-    // ---- stage B on plane z - 1 (tile cells), stencil reads from the ring --
+    // ---- stage B on plane z - 2 (tile cells), stencil reads from the mid ring
     {
-      const int zz = z - 1;
+      const int zz = z - 2;
       const bool active = owner && zz >= z_begin && zz < z_end;
       PmlCell c;
       c.i0 = zz;
@@ -642,31 +736,31 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
       c.idx = pml_lin(zz, i1, i2);
       const int path = pml_warp_path(active, c);
       if (active) {
-        PmlRingSrc rsrc;
-        rsrc.y = a.y;
+        PmlRingSrc<PML_MID_PITCH, PML_MID_PLANE> src;
+        src.y = a.y;
 #pragma unroll
         for (int d = -1; d <= 1; ++d)
-          rsrc.base[d + 1] =
-              ring + (i64)(((zz + d) & 3) * PML_C) * PML_RPLANE + rcell;
+          src.base[d + 1] =
+              mid_ring + (i64)(((zz + d) & 3) * PML_C) * PML_MID_PLANE + mid_cell;
         double K[NK];
-        pml_eval_dt(path, b, rsrc, c, b.t_eval, K);
+        pml_eval_dt(path, b, src, c, b.t_eval, K);
 #pragma unroll
         for (int j = 0; j < PML_NDT; ++j) {
           const int k = PML_DT_IDX[j];
           const i64 o = (i64)k * PML_NCELLS + c.idx;
           if (MODE == PML_F_RK4_12) {
             const double kk = b.dt * K[j];
-            PML_ST(b.acc_out + o, ka_prev[j] + 2.0 * kk);
+            PML_ST(b.acc_out + o, ka_2[j] + 2.0 * kk);
             PML_ST(b.u_out + o,
-                   pml_dirichlet(b, b.dir_slot, k, c, y_prev[j] + kk / 2.0));
+                   pml_dirichlet(b, b.dir_slot, k, c, y_2[j] + kk / 2.0));
           } else if (MODE == PML_F_RK4_34) {
             const double kk = b.dt * K[j];
-            const double acc = PML_LD_ONCE(b.acc_in + o) + 2.0 * ka_prev[j];
+            const double acc = PML_LD_ONCE(b.acc_in + o) + 2.0 * ka_2[j];
             PML_ST(b.y_next + o, pml_dirichlet(b, b.dir_slot, k, c,
-                                               y_prev[j] + (acc + kk) / 6.0));
+                                               y_2[j] + (acc + kk) / 6.0));
           } else {
             PML_ST(b.y_next + o, pml_dirichlet(b, b.dir_slot, k, c,
-                                               y_prev[j] + b.dt * K[j]));
+                                               y_2[j] + b.dt * K[j]));
           }
         }
 #if PML_NALG + PML_NLAP > 0
@@ -683,11 +777,11 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
     }
 #pragma unroll
     for (int j = 0; j < NK; ++j) {
-      ka_prev[j] = ka_new[j];
-      y_prev[j] = y_new[j];
+      ka_2[j] = ka_1[j];
+      y_2[j] = y_1[j];
+      ka_1[j] = ka_new[j];
+      y_1[j] = y_new[j];
     }
-    // no second barrier: the slot stage A writes next, (z + 1) & 3, is not
-    // among the three slots (z - 2, z - 1, z) a lagging warp may still read
   }
 }
 

@@ -332,7 +332,11 @@ int pml_plan_create(const char* source, const pml_plan_desc* desc,
     static const char* fnames[3] = {"pml_fused_rk4_12", "pml_fused_rk4_34",
                                     "pml_fused_mid"};
     const int fbx = desc->fused_block[0], fby = desc->fused_block[1];
-    p->fsmem = 4u * (unsigned)desc->y_dim * (unsigned)(fbx * fby) * 8u;
+    const unsigned mid_plane = (unsigned)(fbx * fby);
+    const unsigned in_plane = desc->n_dims == 3
+                                  ? (unsigned)((fbx + 2) * (fby + 2))
+                                  : (unsigned)(fbx + 2);
+    p->fsmem = 4u * (unsigned)desc->y_dim * (mid_plane + in_plane) * 8u;
     for (int i = 0; i < 3; ++i) {
       r = g_drv.moduleGetFunction(&p->fused[i], p->module, fnames[i]);
       if (r == CUDA_SUCCESS && p->fsmem > 48 * 1024)

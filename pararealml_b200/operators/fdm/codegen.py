@@ -139,7 +139,8 @@ def default_fused(shape, y_dim) -> Optional[Tuple[int, int, int]]:
         fby = 1
     last = shape[-1]
     fbx = max(32, min(fbx, 32 * -(-(last + 2) // 32)))
-    if 4 * y_dim * fbx * fby * 8 > 200 * 1024:
+    in_plane = (fbx + 2) * (fby + 2) if nd == 3 else fbx + 2
+    if 4 * y_dim * (fbx * fby + in_plane) * 8 > 200 * 1024:
         return None
     tiles = -(-last // (fbx - 2))
     if nd == 3:
