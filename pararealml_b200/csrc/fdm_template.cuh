@@ -557,13 +557,40 @@ enum { PML_F_RK4_12 = 0, PML_F_RK4_34 = 1, PML_F_MID = 2 };
 // The slot written in an iteration is never one a lagging warp may still read:
 // in_ring (z+1)&3 == (z-3)&3 vs. stage A(z-1) reading z-2..z; mid_ring z&3 ==
 // (z-4)&3 vs. stage B(z-3) reading z-4..z-2 happens before the barrier.
+// Everything a later stage needs from an earlier plane travels through the
+// rings (the step-start state y rides in the input ring for stages 3+4, stage
+// A's increment k_A and y ride in the mid ring), so no global load sits on the
+// critical path: all of them are issued one plane ahead into registers.
+#define PML_IN_COMPS (PML_C + PML_NDT)       // inputs (+ y for stages 3+4)
+#define PML_MID_COMPS (PML_C + 2 * PML_NDT)  // u_A, k_A, y
+
+// in-plane part of the variant choice (see pml_warp_path): evaluated once per
+// thread block, the marching coordinate only adds a block-uniform condition
+__device__ __forceinline__ int pml_inplane_path(bool active, int i1, int i2) {
+  bool in_all = true, in_outer = true;
+#if PML_NDIM == 3
+  const bool a1 = i1 > 0 && i1 < PML_N1 - 1, a2 = i2 > 0 && i2 < PML_N2 - 1;
+  in_all = a1 && a2;
+  in_outer = a1;
+#else
+  in_all = i1 > 0 && i1 < PML_N1 - 1;
+  in_outer = true;
+#endif
+  if (__all_sync(0xffffffffu, !active || in_all)) return 2;
+  if (__all_sync(0xffffffffu, !active || in_outer)) return 1;
+  return 0;
+}
+
 template <int MODE>
 __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
                                                double* smem) {
   const PmlArgs& a = f.s;
   constexpr bool first = MODE != PML_F_RK4_34;  // stage A's input is y itself
+  constexpr int NK = PML_NDT > 0 ? PML_NDT : 1;
+  constexpr int IN_SLOT = PML_IN_COMPS * PML_IN_PLANE;
+  constexpr int MID_SLOT = PML_MID_COMPS * PML_MID_PLANE;
   double* in_ring = smem;
-  double* mid_ring = smem + 4 * PML_C * PML_IN_PLANE;
+  double* mid_ring = smem + 4 * IN_SLOT;
   const int tx = threadIdx.x;
 #if PML_NDIM == 3
   const int ty = threadIdx.y;
@@ -588,9 +615,10 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
     else { e1 = t - 2 * row - PML_FBY + 1; e2 = PML_FBX + 1; }
   }
   const int x1 = o1 - 1 + e1, x2 = o2 - 1 + e2;  // mesh coords of the extra cell
-  const bool extra = tid < PML_IN_EXTRA && x1 >= 0 && x1 < PML_N1 && x2 >= 0 &&
+  const bool has_extra = tid < PML_IN_EXTRA;
+  const bool extra = has_extra && x1 >= 0 && x1 < PML_N1 && x2 >= 0 &&
                      x2 < PML_N2;
-  const int extra_cell = e1 * PML_IN_PITCH + e2;
+  const int extra_cell = has_extra ? e1 * PML_IN_PITCH + e2 : 0;
 #else
   const int tid = tx;
   const int o1 = blockIdx.x * (PML_FBX - 2) - 1;
@@ -602,8 +630,9 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
   const int chunk = blockIdx.y;
   const int e1 = tid == 0 ? 0 : PML_FBX + 1;
   const int x1 = o1 - 1 + e1, x2 = 0;
-  const bool extra = tid < 2 && x1 >= 0 && x1 < PML_N1;
-  const int extra_cell = e1;
+  const bool has_extra = tid < 2;
+  const bool extra = has_extra && x1 >= 0 && x1 < PML_N1;
+  const int extra_cell = has_extra ? e1 : 0;
 #endif
   const int z_begin = chunk * PML_FZC;
   const int z_end = min(z_begin + PML_FZC, PML_N0);
@@ -617,6 +646,10 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
   b.neu_slot = f.neu_slot_b;
   b.dir_slot = f.dir_slot_b;
 
+  // loop-invariant part of the variant choice
+  const int path_a_in = pml_inplane_path(in_plane, i1, i2);
+  const int path_b_in = pml_inplane_path(owner, i1, i2);
+
   // stage A's stencil input: y (first stages) or the previous stage's output
   const double* IN[PML_C];
 #pragma unroll
@@ -626,9 +659,11 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
   const i64 own_off = pml_lin(0, in_plane ? i1 : 0, in_plane ? i2 : 0);
   const i64 extra_off = pml_lin(0, extra ? x1 : 0, extra ? x2 : 0);
 
-  constexpr int NK = PML_NDT > 0 ? PML_NDT : 1;
-  // prefetch registers: input plane (own + extra cell), step-start state
-  double pre_own[PML_C], pre_extra[PML_C], pre_y[NK];
+  // prefetch registers: one input plane (own + extra cell), the step-start
+  // state for stages 3+4 and the accumulator stage B will need
+  double pre_own[PML_C], pre_extra[PML_C], pre_y[NK], acc_cur[NK];
+#pragma unroll
+  for (int j = 0; j < NK; ++j) pre_y[j] = acc_cur[j] = 0.0;
   auto prefetch = [&](int zp) {
     const bool valid = zp >= zi_lo && zp <= zi_hi;
     const i64 zoff = (i64)zp * PmlAx<0>::S;
@@ -640,21 +675,29 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
       pre_extra[k] = (ring_comp && valid && extra)
                          ? PML_LD(IN[k] + zoff + extra_off) : 0.0;
     }
+    if (!first) {
+#pragma unroll
+      for (int j = 0; j < PML_NDT; ++j)
+        pre_y[j] = (valid && in_plane)
+                       ? PML_LD(a.y + (i64)PML_DT_IDX[j] * PML_NCELLS + zoff +
+                                own_off)
+                       : 0.0;
+    }
   };
   auto deposit = [&](int zp) {
-    double* slot = in_ring + (i64)((zp & 3) * PML_C) * PML_IN_PLANE;
+    double* slot = in_ring + ((zp & 3) * IN_SLOT);
 #pragma unroll
     for (int k = 0; k < PML_C; ++k) {
       if (PML_PASSTHROUGH && PML_KIND[k] != 0) continue;
       slot[k * PML_IN_PLANE + in_cell] = pre_own[k];
-      if (tid < PML_IN_EXTRA) slot[k * PML_IN_PLANE + extra_cell] = pre_extra[k];
+      if (has_extra) slot[k * PML_IN_PLANE + extra_cell] = pre_extra[k];
+    }
+    if (!first) {
+#pragma unroll
+      for (int j = 0; j < PML_NDT; ++j)
+        slot[(PML_C + j) * PML_IN_PLANE + in_cell] = pre_y[j];
     }
   };
-
-  // results of stage A that stage B needs two planes later
-  double ka_1[NK], y_1[NK], ka_2[NK], y_2[NK];
-#pragma unroll
-  for (int j = 0; j < NK; ++j) ka_1[j] = y_1[j] = ka_2[j] = y_2[j] = pre_y[j] = 0.0;
 
   // prologue: planes zi_lo .. za_lo into the ring, za_lo + 1 into registers
   for (int zp = zi_lo; zp <= za_lo; ++zp) {
@@ -663,53 +706,61 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
   }
   prefetch(za_lo + 1);
 
-  for (int z = za_lo; z <= z_end + 1; ++z) {
-    deposit(z + 1);       // plane z + 1 was prefetched during the last iteration
-    prefetch(z + 2);      // consumed in the next iteration
-    if (!first) {
-      // step-start state at the stage-A cell of the NEXT iteration's plane is
-      // not needed early: it is read below together with the ring (cheap,
-      // coalesced, L2 resident after stage 1+2 of the same step)
+  i64 idx_a = pml_lin(za_lo, in_plane ? i1 : 0, in_plane ? i2 : 0);
+  for (int z = za_lo; z <= z_end + 1; ++z, idx_a += PmlAx<0>::S) {
+    deposit(z + 1);   // plane z + 1 was prefetched during the last iteration
+    prefetch(z + 2);  // consumed in the next iteration
+    const int zz = z - 2;  // stage B's plane
+    const bool b_plane = zz >= z_begin && zz < z_end;
+    const i64 idx_b = idx_a - 2 * PmlAx<0>::S;
+    double acc_next[NK];
+#pragma unroll
+    for (int j = 0; j < NK; ++j) acc_next[j] = 0.0;
+    if (MODE == PML_F_RK4_34) {
+      // the accumulator stage B needs in the NEXT iteration (plane z - 1)
+      const bool need = owner && (zz + 1) >= z_begin && (zz + 1) < z_end;
+#pragma unroll
+      for (int j = 0; j < PML_NDT; ++j)
+        acc_next[j] =
+            need ? PML_LD_ONCE(a.acc_in + (i64)PML_DT_IDX[j] * PML_NCELLS +
+                               idx_b + PmlAx<0>::S)
+                 : 0.0;
     }
     __syncthreads();
     // ---- stage A on plane z (halo'd tile), stencil reads from the input ring
-    double ka_new[NK], y_new[NK];
-#pragma unroll
-    for (int j = 0; j < NK; ++j) ka_new[j] = y_new[j] = 0.0;
     {
-      const bool active = in_plane && z >= za_lo && z <= za_hi;
-      PmlCell c;
-      c.i0 = z;
-      c.i1 = i1;
-      c.i2 = i2;
-      c.idx = pml_lin(z, i1, i2);
-      const int path = pml_warp_path(active, c);
+      const bool a_plane = z >= za_lo && z <= za_hi;
+      const bool active = in_plane && a_plane;
+      const int path = (z > 0 && z < PML_N0 - 1) ? path_a_in : 0;
       if (active) {
+        PmlCell c;
+        c.i0 = z;
+        c.i1 = i1;
+        c.i2 = i2;
+        c.idx = idx_a;
         PmlRingSrc<PML_IN_PITCH, PML_IN_PLANE> src;
         src.y = a.y;
 #pragma unroll
         for (int d = -1; d <= 1; ++d)
-          src.base[d + 1] =
-              in_ring + (i64)(((z + d) & 3) * PML_C) * PML_IN_PLANE + in_cell;
+          src.base[d + 1] = in_ring + (((z + d) & 3) * IN_SLOT) + in_cell;
         double K[NK];
         pml_eval_dt(path, a, src, c, a.t_eval, K);
-        double* slot = mid_ring + (i64)((z & 3) * PML_C) * PML_MID_PLANE + mid_cell;
+        double* slot = mid_ring + ((z & 3) * MID_SLOT) + mid_cell;
 #pragma unroll
         for (int j = 0; j < PML_NDT; ++j) {
           const int k = PML_DT_IDX[j];
-          const i64 o = (i64)k * PML_NCELLS + c.idx;
           const double y0 = first ? src.template rel<0, 0, 0>(k, c)
-                                  : PML_LD(a.y + o);
-          double ua;
+                                  : src.base[1][(PML_C + j) * PML_IN_PLANE];
+          double ua, ka = 0.0;
           if (MODE == PML_F_MID) {
             ua = y0 + (a.dt / 2.0) * K[j];
           } else {
-            const double kk = a.dt * K[j];
-            ua = MODE == PML_F_RK4_12 ? y0 + kk / 2.0 : y0 + kk;
-            ka_new[j] = kk;
+            ka = a.dt * K[j];
+            ua = MODE == PML_F_RK4_12 ? y0 + ka / 2.0 : y0 + ka;
           }
-          y_new[j] = y0;
           slot[k * PML_MID_PLANE] = pml_dirichlet(a, a.dir_slot, k, c, ua);
+          slot[(PML_C + j) * PML_MID_PLANE] = ka;
+          slot[(PML_C + PML_NDT + j) * PML_MID_PLANE] = y0;
         }
 #if PML_NALG + PML_NLAP > 0
         if (!PML_PASSTHROUGH) {
@@ -727,40 +778,40 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
     }
     // ---- stage B on plane z - 2 (tile cells), stencil reads from the mid ring
     {
-      const int zz = z - 2;
-      const bool active = owner && zz >= z_begin && zz < z_end;
-      PmlCell c;
-      c.i0 = zz;
-      c.i1 = i1;
-      c.i2 = i2;
-      c.idx = pml_lin(zz, i1, i2);
-      const int path = pml_warp_path(active, c);
+      const bool active = owner && b_plane;
+      const int path = (zz > 0 && zz < PML_N0 - 1) ? path_b_in : 0;
       if (active) {
+        PmlCell c;
+        c.i0 = zz;
+        c.i1 = i1;
+        c.i2 = i2;
+        c.idx = idx_b;
         PmlRingSrc<PML_MID_PITCH, PML_MID_PLANE> src;
         src.y = a.y;
 #pragma unroll
         for (int d = -1; d <= 1; ++d)
-          src.base[d + 1] =
-              mid_ring + (i64)(((zz + d) & 3) * PML_C) * PML_MID_PLANE + mid_cell;
+          src.base[d + 1] = mid_ring + (((zz + d) & 3) * MID_SLOT) + mid_cell;
         double K[NK];
         pml_eval_dt(path, b, src, c, b.t_eval, K);
 #pragma unroll
         for (int j = 0; j < PML_NDT; ++j) {
           const int k = PML_DT_IDX[j];
           const i64 o = (i64)k * PML_NCELLS + c.idx;
+          const double ka = src.base[1][(PML_C + j) * PML_MID_PLANE];
+          const double y0 = src.base[1][(PML_C + PML_NDT + j) * PML_MID_PLANE];
           if (MODE == PML_F_RK4_12) {
             const double kk = b.dt * K[j];
-            PML_ST(b.acc_out + o, ka_2[j] + 2.0 * kk);
+            PML_ST(b.acc_out + o, ka + 2.0 * kk);
             PML_ST(b.u_out + o,
-                   pml_dirichlet(b, b.dir_slot, k, c, y_2[j] + kk / 2.0));
+                   pml_dirichlet(b, b.dir_slot, k, c, y0 + kk / 2.0));
           } else if (MODE == PML_F_RK4_34) {
             const double kk = b.dt * K[j];
-            const double acc = PML_LD_ONCE(b.acc_in + o) + 2.0 * ka_2[j];
-            PML_ST(b.y_next + o, pml_dirichlet(b, b.dir_slot, k, c,
-                                               y_2[j] + (acc + kk) / 6.0));
+            const double acc = acc_cur[j] + 2.0 * ka;
+            PML_ST(b.y_next + o,
+                   pml_dirichlet(b, b.dir_slot, k, c, y0 + (acc + kk) / 6.0));
           } else {
-            PML_ST(b.y_next + o, pml_dirichlet(b, b.dir_slot, k, c,
-                                               y_2[j] + b.dt * K[j]));
+            PML_ST(b.y_next + o,
+                   pml_dirichlet(b, b.dir_slot, k, c, y0 + b.dt * K[j]));
           }
         }
 #if PML_NALG + PML_NLAP > 0
@@ -776,12 +827,7 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
       }
     }
 #pragma unroll
-    for (int j = 0; j < NK; ++j) {
-      ka_2[j] = ka_1[j];
-      y_2[j] = y_1[j];
-      ka_1[j] = ka_new[j];
-      y_1[j] = y_new[j];
-    }
+    for (int j = 0; j < NK; ++j) acc_cur[j] = acc_next[j];
   }
 }
 

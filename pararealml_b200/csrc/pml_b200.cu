@@ -140,10 +140,13 @@ struct PmlJacobiArgs {
   const int* done;
 };
 
-int nvrtc_compile(const char* source, std::vector<char>& cubin) {
+// `name` is the file name recorded in the line info; when it is a real path the
+// generated source is also written there so that profilers can show it
+int nvrtc_compile(const char* source, std::vector<char>& cubin,
+                  const char* name = "pml_generated.cu") {
   nvrtcProgram prog;
-  if (nvrtcCreateProgram(&prog, source, "pml_generated.cu", 0, nullptr,
-                         nullptr) != NVRTC_SUCCESS)
+  if (nvrtcCreateProgram(&prog, source, name, 0, nullptr, nullptr) !=
+      NVRTC_SUCCESS)
     return fail("nvrtcCreateProgram failed");
   const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17",
                         "-lineinfo", "--fmad=true"};
@@ -287,7 +290,10 @@ int pml_version(void) { return 100; }
 
 int pml_compile_to_cubin(const char* source, const char* cubin_path) {
   std::vector<char> cubin;
-  if (nvrtc_compile(source, cubin)) return -1;
+  std::string src_path = std::string(cubin_path) + ".cu";
+  std::vector<char> text(source, source + std::strlen(source));
+  write_file(src_path.c_str(), text);
+  if (nvrtc_compile(source, cubin, src_path.c_str())) return -1;
   if (!write_file(cubin_path, cubin))
     return fail(std::string("cannot write ") + cubin_path);
   return 0;
@@ -299,8 +305,15 @@ int pml_plan_create(const char* source, const pml_plan_desc* desc,
   if (load_driver()) return -1;
   std::vector<char> cubin;
   bool cached = cubin_path && read_file(cubin_path, cubin);
+  std::string src_path = cubin_path ? std::string(cubin_path) + ".cu" : "";
   if (!cached) {
-    if (nvrtc_compile(source, cubin)) return -1;
+    if (cubin_path) {
+      std::vector<char> text(source, source + std::strlen(source));
+      write_file(src_path.c_str(), text);
+    }
+    if (nvrtc_compile(source, cubin,
+                      cubin_path ? src_path.c_str() : "pml_generated.cu"))
+      return -1;
     if (cubin_path) write_file(cubin_path, cubin);
   }
   pml_plan* p = new pml_plan();
@@ -336,13 +349,21 @@ int pml_plan_create(const char* source, const pml_plan_desc* desc,
     const unsigned in_plane = desc->n_dims == 3
                                   ? (unsigned)((fbx + 2) * (fby + 2))
                                   : (unsigned)(fbx + 2);
-    p->fsmem = 4u * (unsigned)desc->y_dim * (mid_plane + in_plane) * 8u;
+    // input ring: y_dim (+ n_dt for the step-start state) planes per slot;
+    // mid ring: y_dim + 2 n_dt (stage-A state, its increment, y)
+    const unsigned in_comps = (unsigned)(desc->y_dim + desc->n_dt);
+    const unsigned mid_comps = (unsigned)(desc->y_dim + 2 * desc->n_dt);
+    p->fsmem = 4u * (in_comps * in_plane + mid_comps * mid_plane) * 8u;
     for (int i = 0; i < 3; ++i) {
       r = g_drv.moduleGetFunction(&p->fused[i], p->module, fnames[i]);
       if (r == CUDA_SUCCESS && p->fsmem > 48 * 1024)
         r = g_drv.funcSetAttribute(
             p->fused[i], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
             (int)p->fsmem);
+      if (r == CUDA_SUCCESS)
+        r = g_drv.funcSetAttribute(
+            p->fused[i], CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT,
+            100);
       if (r != CUDA_SUCCESS) {
         std::string m = std::string("fused kernel unavailable: ") + fnames[i] +
                         ": " + cu_err(r);

@@ -118,7 +118,7 @@ def default_small(shape) -> int:
     return int(min(1024, max(32, 32 * -(-cells // 32))))
 
 
-def default_fused(shape, y_dim) -> Optional[Tuple[int, int, int]]:
+def default_fused(shape, y_dim, n_dt=None) -> Optional[Tuple[int, int, int]]:
     """Tile of the fused stage-pair kernels (csrc/fdm_template.cuh): threads
     cover the tile plus a one-cell halo ring; planes per chunk are chosen so
     that the grid has several waves of thread blocks."""
@@ -140,7 +140,9 @@ def default_fused(shape, y_dim) -> Optional[Tuple[int, int, int]]:
     last = shape[-1]
     fbx = max(32, min(fbx, 32 * -(-(last + 2) // 32)))
     in_plane = (fbx + 2) * (fby + 2) if nd == 3 else fbx + 2
-    if 4 * y_dim * (fbx * fby + in_plane) * 8 > 200 * 1024:
+    n_dt = y_dim if n_dt is None else n_dt
+    smem = 4 * 8 * ((y_dim + n_dt) * in_plane + (y_dim + 2 * n_dt) * fbx * fby)
+    if smem > 200 * 1024:
         return None
     tiles = -(-last // (fbx - 2))
     if nd == 3:

@@ -73,7 +73,9 @@ def plan_overrides(cp, low: LoweredProblem, y0: Optional[np.ndarray]) -> dict:
             passthrough = bool(np.array_equal(probe, y0))
     return {
         "passthrough": passthrough,
-        "fused": codegen.default_fused(low.shape, low.y_dim),
+        "fused": codegen.default_fused(
+            low.shape, low.y_dim, len(low.kind_indices("D_Y_OVER_D_T"))
+        ),
         "small_threads": codegen.default_small(low.shape),
     }
 

@@ -120,3 +120,30 @@ def test_solve_on_device_keeps_the_trajectory_in_hbm():
     planes = traj.cpu().numpy().reshape(len(t), 3, n)
     y = np.moveaxis(planes, 1, 2).reshape((len(t), 12, 12, 12, 3))
     assert per_step_rel_err(y[g["steps"]], g["y"]) <= 1e-12
+
+
+@pytest.mark.parametrize(
+    "case_name",
+    ["diffusion_2d_rk4", "wave_2d_dynamic_mid", "cahn_hilliard_3d_rk4",
+     "all_leaves_3d_spherical_mid", "navier_stokes_2d_rk4", "lorenz_rk4"],
+)
+def test_kernel_variants_agree(case_name, monkeypatch):
+    """The three execution strategies of the stage arithmetic -- one launch
+    per stage, fused stage pairs (shared-memory plane rings) and the
+    single-block time loop for small meshes -- give the same trajectory."""
+    case = cases.FDM_BY_NAME[case_name]
+    results = {}
+    for name, env in (
+        ("per_stage", {"PML_SMALL": "0", "PML_FUSE": "0"}),
+        ("fused", {"PML_SMALL": "0", "PML_FUSE": "1"}),
+        ("single_block", {"PML_SMALL": "1", "PML_FUSE": "0"}),
+    ):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        ivp = case.build(ns)
+        if case.seed is not None:
+            np.random.seed(case.seed)
+        results[name] = make_operator(case).solve(ivp).discrete_y()
+    tol = 1e-9 if "jacobi" in case.tags else 1e-13
+    assert per_step_rel_err(results["fused"], results["per_stage"]) <= tol
+    assert per_step_rel_err(results["single_block"], results["per_stage"]) <= tol
