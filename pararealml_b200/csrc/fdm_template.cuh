@@ -557,12 +557,12 @@ enum { PML_F_RK4_12 = 0, PML_F_RK4_34 = 1, PML_F_MID = 2 };
 // The slot written in an iteration is never one a lagging warp may still read:
 // in_ring (z+1)&3 == (z-3)&3 vs. stage A(z-1) reading z-2..z; mid_ring z&3 ==
 // (z-4)&3 vs. stage B(z-3) reading z-4..z-2 happens before the barrier.
-// Everything a later stage needs from an earlier plane travels through the
-// rings (the step-start state y rides in the input ring for stages 3+4, stage
-// A's increment k_A and y ride in the mid ring), so no global load sits on the
-// critical path: all of them are issued one plane ahead into registers.
-#define PML_IN_COMPS (PML_C + PML_NDT)       // inputs (+ y for stages 3+4)
-#define PML_MID_COMPS (PML_C + 2 * PML_NDT)  // u_A, k_A, y
+// No global load sits on the critical path: the input plane, the step-start
+// state (stages 3+4) and the accumulator are all requested one plane ahead
+// into registers; stage A's increment k_A and y travel to stage B (two planes
+// later) in registers.
+#define PML_IN_COMPS (PML_C)
+#define PML_MID_COMPS (PML_C)
 
 // in-plane part of the variant choice (see pml_warp_path): evaluated once per
 // thread block, the marching coordinate only adds a block-uniform condition
@@ -675,14 +675,16 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
       pre_extra[k] = (ring_comp && valid && extra)
                          ? PML_LD(IN[k] + zoff + extra_off) : 0.0;
     }
-    if (!first) {
+  };
+  // step-start state at this thread's stage-A cell of plane zp (stages 3+4)
+  auto prefetch_y = [&](int zp, double* dst) {
+    const bool valid = zp >= za_lo && zp <= za_hi && in_plane;
+    const i64 zoff = (i64)zp * PmlAx<0>::S;
 #pragma unroll
-      for (int j = 0; j < PML_NDT; ++j)
-        pre_y[j] = (valid && in_plane)
-                       ? PML_LD(a.y + (i64)PML_DT_IDX[j] * PML_NCELLS + zoff +
-                                own_off)
-                       : 0.0;
-    }
+    for (int j = 0; j < PML_NDT; ++j)
+      dst[j] = valid ? PML_LD(a.y + (i64)PML_DT_IDX[j] * PML_NCELLS + zoff +
+                              own_off)
+                     : 0.0;
   };
   auto deposit = [&](int zp) {
     double* slot = in_ring + ((zp & 3) * IN_SLOT);
@@ -692,11 +694,6 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
       slot[k * PML_IN_PLANE + in_cell] = pre_own[k];
       if (has_extra) slot[k * PML_IN_PLANE + extra_cell] = pre_extra[k];
     }
-    if (!first) {
-#pragma unroll
-      for (int j = 0; j < PML_NDT; ++j)
-        slot[(PML_C + j) * PML_IN_PLANE + in_cell] = pre_y[j];
-    }
   };
 
   // prologue: planes zi_lo .. za_lo into the ring, za_lo + 1 into registers
@@ -705,6 +702,12 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
     deposit(zp);
   }
   prefetch(za_lo + 1);
+  if (!first) prefetch_y(za_lo, pre_y);
+
+  // stage-A results stage B needs two planes later
+  double ka_1[NK], y_1[NK], ka_2[NK], y_2[NK];
+#pragma unroll
+  for (int j = 0; j < NK; ++j) ka_1[j] = y_1[j] = ka_2[j] = y_2[j] = 0.0;
 
   i64 idx_a = pml_lin(za_lo, in_plane ? i1 : 0, in_plane ? i2 : 0);
   for (int z = za_lo; z <= z_end + 1; ++z, idx_a += PmlAx<0>::S) {
@@ -713,9 +716,11 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
     const int zz = z - 2;  // stage B's plane
     const bool b_plane = zz >= z_begin && zz < z_end;
     const i64 idx_b = idx_a - 2 * PmlAx<0>::S;
-    double acc_next[NK];
+    double acc_next[NK], y_next_plane[NK], ka_new[NK], y_new[NK];
 #pragma unroll
-    for (int j = 0; j < NK; ++j) acc_next[j] = 0.0;
+    for (int j = 0; j < NK; ++j)
+      acc_next[j] = y_next_plane[j] = ka_new[j] = y_new[j] = 0.0;
+    if (!first) prefetch_y(z + 1, y_next_plane);
     if (MODE == PML_F_RK4_34) {
       // the accumulator stage B needs in the NEXT iteration (plane z - 1)
       const bool need = owner && (zz + 1) >= z_begin && (zz + 1) < z_end;
@@ -749,8 +754,7 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
 #pragma unroll
         for (int j = 0; j < PML_NDT; ++j) {
           const int k = PML_DT_IDX[j];
-          const double y0 = first ? src.template rel<0, 0, 0>(k, c)
-                                  : src.base[1][(PML_C + j) * PML_IN_PLANE];
+          const double y0 = first ? src.template rel<0, 0, 0>(k, c) : pre_y[j];
           double ua, ka = 0.0;
           if (MODE == PML_F_MID) {
             ua = y0 + (a.dt / 2.0) * K[j];
@@ -759,8 +763,8 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
             ua = MODE == PML_F_RK4_12 ? y0 + ka / 2.0 : y0 + ka;
           }
           slot[k * PML_MID_PLANE] = pml_dirichlet(a, a.dir_slot, k, c, ua);
-          slot[(PML_C + j) * PML_MID_PLANE] = ka;
-          slot[(PML_C + PML_NDT + j) * PML_MID_PLANE] = y0;
+          ka_new[j] = ka;
+          y_new[j] = y0;
         }
 #if PML_NALG + PML_NLAP > 0
         if (!PML_PASSTHROUGH) {
@@ -797,8 +801,7 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
         for (int j = 0; j < PML_NDT; ++j) {
           const int k = PML_DT_IDX[j];
           const i64 o = (i64)k * PML_NCELLS + c.idx;
-          const double ka = src.base[1][(PML_C + j) * PML_MID_PLANE];
-          const double y0 = src.base[1][(PML_C + PML_NDT + j) * PML_MID_PLANE];
+          const double ka = ka_2[j], y0 = y_2[j];
           if (MODE == PML_F_RK4_12) {
             const double kk = b.dt * K[j];
             PML_ST(b.acc_out + o, ka + 2.0 * kk);
@@ -827,7 +830,14 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
       }
     }
 #pragma unroll
-    for (int j = 0; j < NK; ++j) acc_cur[j] = acc_next[j];
+    for (int j = 0; j < NK; ++j) {
+      acc_cur[j] = acc_next[j];
+      pre_y[j] = y_next_plane[j];
+      ka_2[j] = ka_1[j];
+      y_2[j] = y_1[j];
+      ka_1[j] = ka_new[j];
+      y_1[j] = y_new[j];
+    }
   }
 }
 

@@ -349,10 +349,9 @@ int pml_plan_create(const char* source, const pml_plan_desc* desc,
     const unsigned in_plane = desc->n_dims == 3
                                   ? (unsigned)((fbx + 2) * (fby + 2))
                                   : (unsigned)(fbx + 2);
-    // input ring: y_dim (+ n_dt for the step-start state) planes per slot;
-    // mid ring: y_dim + 2 n_dt (stage-A state, its increment, y)
-    const unsigned in_comps = (unsigned)(desc->y_dim + desc->n_dt);
-    const unsigned mid_comps = (unsigned)(desc->y_dim + 2 * desc->n_dt);
+    // 4 slots of y_dim planes in each of the two rings
+    const unsigned in_comps = (unsigned)desc->y_dim;
+    const unsigned mid_comps = (unsigned)desc->y_dim;
     p->fsmem = 4u * (in_comps * in_plane + mid_comps * mid_plane) * 8u;
     for (int i = 0; i < 3; ++i) {
       r = g_drv.moduleGetFunction(&p->fused[i], p->module, fnames[i]);

@@ -141,7 +141,7 @@ def default_fused(shape, y_dim, n_dt=None) -> Optional[Tuple[int, int, int]]:
     fbx = max(32, min(fbx, 32 * -(-(last + 2) // 32)))
     in_plane = (fbx + 2) * (fby + 2) if nd == 3 else fbx + 2
     n_dt = y_dim if n_dt is None else n_dt
-    smem = 4 * 8 * ((y_dim + n_dt) * in_plane + (y_dim + 2 * n_dt) * fbx * fby)
+    smem = 4 * 8 * y_dim * (in_plane + fbx * fby)
     if smem > 200 * 1024:
         return None
     tiles = -(-last // (fbx - 2))
