@@ -31,6 +31,7 @@ typedef struct pml_plan_desc {
   int fused_block[2]; /* their thread block (contiguous axis, axis 1) */
   int fused_zc;     /* planes of the marching axis per thread block */
   int small_threads; /* > 0: the source has the single-block time loop kernel */
+  int zrep;         /* cells along axis 0 per thread in the stage kernels */
 } pml_plan_desc;
 
 /* NaN-coded boundary tables and 1-D coordinate vectors (device pointers).

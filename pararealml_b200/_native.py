@@ -35,6 +35,7 @@ class PlanDesc(Structure):
         ("fused_block", c_int * 2),
         ("fused_zc", c_int),
         ("small_threads", c_int),
+        ("zrep", c_int),
     ]
 
 

@@ -468,13 +468,38 @@ __device__ __forceinline__ bool pml_this_cell(PmlCell& c) {
   return true;
 }
 
+// stage kernels: every thread walks PML_ZREP consecutive cells along axis 0
+// (fewer, longer-lived thread blocks; the plane loaded as the upper neighbour
+// of one cell is the centre of the next and stays in L1)
+__device__ __forceinline__ bool pml_stage_cell_coords(PmlCell& c, int rep) {
+#if PML_NDIM <= 1
+  (void)rep;
+  return pml_this_cell(c);
+#elif PML_NDIM == 2
+  c.i1 = blockIdx.x * PML_BX + threadIdx.x;
+  c.i0 = (blockIdx.y * PML_ZREP + rep) * PML_BY + threadIdx.y;
+  c.i2 = 0;
+  c.idx = pml_lin(c.i0, c.i1, 0);
+  return c.i1 < PML_N1 && c.i0 < PML_N0;
+#else
+  c.i2 = blockIdx.x * PML_BX + threadIdx.x;
+  c.i1 = blockIdx.y * PML_BY + threadIdx.y;
+  c.i0 = (blockIdx.z * PML_ZREP + rep) * PML_BZ + threadIdx.z;
+  c.idx = pml_lin(c.i0, c.i1, c.i2);
+  return c.i2 < PML_N2 && c.i1 < PML_N1 && c.i0 < PML_N0;
+#endif
+}
+
 #define PML_STAGE_KERNEL(NAME, STAGE)                                      \
   extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ,     \
                                                PML_MIN_BLOCKS)             \
       NAME(const __grid_constant__ PmlArgs a) {                            \
-    PmlCell c;                                                             \
-    const bool active = pml_this_cell(c);                                  \
-    pml_stage_cell<STAGE>(a, active, c);                                   \
+    _Pragma("unroll 1") for (int rep = 0;                                  \
+                             rep < (PML_NDIM <= 1 ? 1 : PML_ZREP); ++rep) { \
+      PmlCell c;                                                           \
+      const bool active = pml_stage_cell_coords(c, rep);                   \
+      pml_stage_cell<STAGE>(a, active, c);                                 \
+    }                                                                      \
   }
 
 PML_STAGE_KERNEL(pml_stage_fe, PML_FE)

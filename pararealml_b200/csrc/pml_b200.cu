@@ -202,6 +202,7 @@ struct pml_plan {
              jac_store = nullptr;
   pml_tables tables{};
   dim3 grid, block;
+  dim3 sgrid;  // grid of the stage kernels (zrep cells along axis 0 per thread)
   long long n_cells = 0;
   long long n_blocks = 0;
   long long launches = 0;
@@ -414,6 +415,12 @@ int pml_plan_create(const char* source, const pml_plan_desc* desc,
     p->grid = dim3(cdiv(n[1], b[0]), cdiv(n[0], b[1]), 1);
   else
     p->grid = dim3(cdiv(n[2], b[0]), cdiv(n[1], b[1]), cdiv(n[0], b[2]));
+  p->sgrid = p->grid;
+  const int zrep = desc->zrep > 1 ? desc->zrep : 1;
+  if (desc->n_dims == 2)
+    p->sgrid.y = cdiv(n[0], b[1] * zrep);
+  else if (desc->n_dims == 3)
+    p->sgrid.z = cdiv(n[0], b[2] * zrep);
   p->n_cells = (long long)n[0] * n[1] * n[2];
   p->n_blocks = (long long)p->grid.x * p->grid.y * p->grid.z;
   *out = p;
@@ -499,7 +506,12 @@ int pml_fdm_run(pml_plan* p, int integrator, const pml_workspace* ws,
       a.t_eval = t_eval;
       a.neu_slot = neu_slot;
       a.dir_slot = dir_slot;
-      return launch(p, p->stage[k], params, s);
+      CUresult r_ = g_drv.launchKernel(p->stage[k], p->sgrid.x, p->sgrid.y,
+                                       p->sgrid.z, p->block.x, p->block.y,
+                                       p->block.z, 0, s, params, nullptr);
+      if (r_ != CUDA_SUCCESS) return fail("stage launch: " + cu_err(r_));
+      p->launches += 1;
+      return 0;
     };
     auto fused = [&](int k, const double* u, double* u_out, double t_a,
                      long long neu_a, long long dir_a, double t_b,

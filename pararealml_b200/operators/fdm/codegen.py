@@ -91,6 +91,8 @@ class ProblemSpec:
     fused: Optional[Tuple[int, int, int]] = None
     #: threads of the single-block time-loop kernel for small meshes (0: none)
     small_threads: int = 0
+    #: cells along axis 0 every thread of a stage kernel walks
+    zrep: int = 1
 
 
 def default_block(shape) -> Tuple[int, int, int]:
@@ -105,6 +107,15 @@ def default_block(shape) -> Tuple[int, int, int]:
 
 N_SMS = 148
 SMALL_MESH_CELLS = 8192
+
+
+def default_zrep(shape) -> int:
+    """Cells along axis 0 per thread in the stage kernels (2-D / 3-D meshes)."""
+    if len(shape) < 2:
+        return 1
+    if os.environ.get("PML_ZREP"):
+        return max(1, int(os.environ["PML_ZREP"]))
+    return 8 if shape[0] >= 64 else 1
 
 
 def default_small(shape) -> int:
@@ -505,6 +516,7 @@ def generate_source(spec: ProblemSpec) -> str:
         f"#define PML_FBY {fused[1] if fused else 1}",
         f"#define PML_FZC {fused[2] if fused else 1}",
         f"#define PML_FMIN_BLOCKS {fmin if fused else 1}",
+        f"#define PML_ZREP {max(1, int(spec.zrep))}",
         f"#define PML_BX {block[0]}",
         f"#define PML_BY {block[1]}",
         f"#define PML_BZ {block[2]}",

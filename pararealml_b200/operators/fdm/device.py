@@ -83,6 +83,7 @@ class DevicePlan:
             desc.fused_zc = fused[2]
         self.fused = fused
         desc.small_threads = int(spec.small_threads)
+        desc.zrep = max(1, int(spec.zrep))
         desc.y_dim = low.y_dim
         desc.n_dt = len(low.kind_indices("D_Y_OVER_D_T"))
         desc.n_alg = len(low.kind_indices("Y"))

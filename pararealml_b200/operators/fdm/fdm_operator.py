@@ -77,6 +77,7 @@ def plan_overrides(cp, low: LoweredProblem, y0: Optional[np.ndarray]) -> dict:
             low.shape, low.y_dim, len(low.kind_indices("D_Y_OVER_D_T"))
         ),
         "small_threads": codegen.default_small(low.shape),
+        "zrep": codegen.default_zrep(low.shape),
     }
 
 
