@@ -303,6 +303,16 @@ __device__ __forceinline__ int pml_interior_mask(const PmlCell& c) {
   return m;
 }
 
+// x / 6.0 without the compiler's division subroutine (its call serialises the
+// surrounding loads): Markstein's sequence q = x c, r = x - 6 q (exact, FMA),
+// q + r c is the correctly rounded quotient throughout the normal range
+__device__ __forceinline__ double pml_div6(double x) {
+  const double c = 1.0 / 6.0;
+  const double q = x * c;
+  const double r = fma(-6.0, q, x);
+  return fma(r, c, q);
+}
+
 // ---------------------------------------------------------------------------
 // generated right-hand sides (prelude declares, generator defines below)
 // ---------------------------------------------------------------------------
@@ -426,7 +436,7 @@ __device__ __forceinline__ void pml_stage_cell(const PmlArgs& a, bool active,
       } else {
         PML_ST(a.y_next + o,
                pml_dirichlet(a, a.dir_slot, k, c,
-                             y0 + (PML_LD_ONCE(a.acc_in + o) + kk) / 6.0));
+                             y0 + pml_div6(PML_LD_ONCE(a.acc_in + o) + kk)));
       }
     }
   }
@@ -836,7 +846,7 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
             const double kk = b.dt * K[j];
             const double acc = acc_cur[j] + 2.0 * ka;
             PML_ST(b.y_next + o,
-                   pml_dirichlet(b, b.dir_slot, k, c, y0 + (acc + kk) / 6.0));
+                   pml_dirichlet(b, b.dir_slot, k, c, y0 + pml_div6(acc + kk)));
           } else {
             PML_ST(b.y_next + o,
                    pml_dirichlet(b, b.dir_slot, k, c, y0 + b.dt * K[j]));
