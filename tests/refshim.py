@@ -113,8 +113,10 @@ def install():
         sys.modules["mpi4py"] = mpi4py
         sys.modules["mpi4py.MPI"] = mpi
 
+    # appended, not prepended: the reference checkout has its own ``tests``
+    # package, which must not shadow this repo's in spawned worker processes
     if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+        sys.path.append(REFERENCE_ROOT)
     import pararealml  # noqa: F401
 
     return pararealml
