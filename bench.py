@@ -53,6 +53,8 @@ def parse_args():
                    help="coarse step = ratio * fine step")
     p.add_argument("--parareal-tol", type=float, default=1e-7)
     p.add_argument("--cpu-grid", type=int, default=96)
+    p.add_argument("--cpu-parareal-grid", type=int, default=48,
+                   help="vertices per axis of the host-process Parareal sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     return p.parse_args()
@@ -291,9 +293,111 @@ def load_traffic():
 # ---------------------------------------------------------------------------
 # reference arm
 # ---------------------------------------------------------------------------
+def _reference_parareal_worker(rank, world, port, n, slice_steps, ratio, tol,
+                               steps, warmup, out):
+    """One host process = one time slice of the reference's mpirun layout."""
+    import torch.distributed as dist
+
+    import oracle
+    import pararealml_b200 as ns
+    from oracle.parareal_ranks import GlooComm, parareal_rank_solve
+
+    dist.init_process_group(
+        "gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world
+    )
+    ivp, d_t = burgers_problem(ns, n, world * slice_steps)
+    f = oracle.OracleFDMOperator("rk4", d_t)
+    g = oracle.OracleFDMOperator("forward_euler", d_t * ratio)
+    comm = GlooComm()
+
+    def sub_ivp(cp, interval, y0):
+        return ns.InitialValueProblem(
+            cp, interval, ns.DiscreteInitialCondition(cp, y0, True)
+        )
+
+    iterations = 0
+    for _ in range(warmup):
+        parareal_rank_solve(comm, ivp, f, g, tol, sub_ivp)
+    comm.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        _, _, iterations = parareal_rank_solve(comm, ivp, f, g, tol, sub_ivp)
+    comm.barrier()
+    if rank == 0:
+        out.put((time.perf_counter() - t0, iterations))
+    dist.destroy_process_group()
+
+
+def run_reference_parareal(args):
+    """N > 1: the reference's Parareal (oracle port, SPMD with Allgathers) on
+    N host processes -- the stand-in for ``mpirun -n N`` (no MPI runtime in
+    the image)."""
+    import socket
+
+    import torch.multiprocessing as mp
+
+    world = args.gpus
+    n = args.cpu_parareal_grid
+    with socket.socket() as sock:
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    mp.spawn(
+        _reference_parareal_worker,
+        args=(world, port, n, args.slice_steps, args.coarse_ratio,
+              args.parareal_tol, args.steps, args.warmup, out),
+        nprocs=world, join=True,
+    )
+    dt, iterations = out.get()
+    total_steps = world * args.slice_steps
+    value = n**3 * total_steps * args.steps / dt / 1e9
+    sample = (
+        f"oracle port of the reference PararealOperator (f = NumPy FDM RK4, "
+        f"g = ForwardEuler at {args.coarse_ratio} d_t) on {world} host "
+        f"processes (gloo Allgather standing in for mpirun; "
+        f"{os.cpu_count()} host cores), 3-D Burgers on {n}^3 (bounded sample "
+        f"of the 512^3 workload), {world} slices x {args.slice_steps} fine "
+        f"steps, {iterations} Parareal iterations per solve"
+    )
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": {
+            "workload": f"PararealOperator(f=FDM RK4 d_t, g=FDM ForwardEuler "
+                        f"{args.coarse_ratio} d_t) on 3-D Burgers, {n}^3 sample "
+                        f"of the 512^3 workload, {world} time slices x "
+                        f"{args.slice_steps} fine steps, tol {args.parareal_tol}",
+            "parareal_iterations": iterations,
+        },
+        "cpu_baseline": {
+            "value": value, "unit": UNIT, "cores": world, "kind": "port",
+            "sample": sample,
+        },
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if args.gpus > 1:
+        run_reference_parareal(args)
         return
     import oracle
     import pararealml_b200 as ns
@@ -522,23 +626,32 @@ def run_b200(args):
 
     e2e = None
     if not args.no_e2e:
-        pe = PararealOperator(f, g, args.parareal_tol)  # gathers to every rank
+        # the reference's final Allgather would put the whole trajectory
+        # (world x slice_steps x 3.2 GB) on every rank; the trajectory stays
+        # sharded instead and every rank reads back its own time slice
+        pe = PararealOperator(f, g, args.parareal_tol, gather_trajectory=False)
+        state_bytes = cells * y_dim * 8
+        host = torch.empty((s_steps, y_dim * cells), dtype=torch.float64,
+                           pin_memory=True)
         barrier()
         t0 = time.perf_counter()
         sol = pe.solve(ivp)
+        host.copy_(pe.last_slice_trajectory, non_blocking=True)
         barrier()
         dt_e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         dist.all_reduce(dt_e, op=dist.ReduceOp.MAX)
-        state_bytes = cells * y_dim * 8
         e2e = {
             "value": cells * total_steps / float(dt_e.item()) / 1e9,
             "unit": UNIT,
-            "h2d_bytes_per_step": state_bytes,
+            "h2d_bytes_per_step": state_bytes * world,
             "d2h_bytes_per_step": state_bytes * total_steps,
-            "note": "PararealOperator.solve(ivp) incl. H2D of y0 and the "
-                    "all-gather + D2H of the full trajectory on every rank",
+            "note": "PararealOperator(gather_trajectory=False).solve(ivp): "
+                    "H2D of y0 on every rank, Parareal iterations, D2H of "
+                    "every rank's own slice of the trajectory (component "
+                    "planes) into pinned host memory; bytes are whole-job "
+                    "totals per solve",
         }
-        del sol
+        del sol, host
     if rank == 0:
         value = cells * total_steps * args.steps / (ms * 1e-3) / 1e9
         line = {

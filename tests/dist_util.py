@@ -21,6 +21,10 @@ def _entry(rank, world_size, port, backend, fn, args, errors):
         if p not in sys.path:
             sys.path.insert(0, p)
     try:
+        if backend == "nccl":
+            import torch
+
+            torch.cuda.set_device(rank % torch.cuda.device_count())
         dist.init_process_group(
             backend, init_method=f"tcp://127.0.0.1:{port}", rank=rank,
             world_size=world_size,

@@ -70,6 +70,28 @@ def test_device_parareal_multi_rank_on_one_gpu(case_name, world_size):
     run_distributed(_worker, world_size, (case_name,))
 
 
+def _nccl_worker(rank, world_size, case_name):
+    import torch
+
+    assert torch.cuda.current_device() == rank
+    case, p, sol = _solve(case_name, world_size)
+    _check(case, p, sol, world_size)
+    assert p.last_slice_trajectory.device.index == rank
+
+
+@pytest.mark.parametrize("case_name", CASES[1:])
+def test_device_parareal_nccl_one_rank_per_gpu(case_name):
+    """The production layout: one rank per GPU, NCCL send/recv of the slice
+    states and an NCCL all-reduce(MAX) convergence check (needs >= 2 GPUs)."""
+    import torch
+
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world_size = 4 if n >= 4 else 2
+    run_distributed(_nccl_worker, world_size, (case_name,), backend="nccl")
+
+
 def test_lazy_sharded_trajectory():
     case, p, sol = _solve("parareal_burgers_3d", 1, gather=False)
     _check(case, p, sol, 1)

@@ -40,6 +40,39 @@ def test_parareal_matches_reference_on_gloo_ranks(case_name, world_size):
     run_distributed(_worker, world_size, (case_name,))
 
 
+def _spmd_oracle_worker(rank, world_size, case_name):
+    import oracle
+    import pararealml_b200 as ns
+    from common import load_golden, per_step_rel_err
+    from golden import cases
+    from oracle.parareal_ranks import GlooComm, parareal_rank_solve
+
+    case = cases.PARAREAL_BY_NAME[case_name]
+    g = load_golden(case.name)
+    ivp = case.build(ns)
+
+    def sub_ivp(cp, interval, y0):
+        return ns.InitialValueProblem(
+            cp, interval, ns.DiscreteInitialCondition(cp, y0, True)
+        )
+
+    _, y, iterations = parareal_rank_solve(
+        GlooComm(), ivp, oracle.OracleFDMOperator(*case.f),
+        oracle.OracleFDMOperator(*case.g), case.tol, sub_ivp,
+    )
+    assert iterations == int(g[f"iterations_{world_size}"])
+    err = per_step_rel_err(y[g[f"steps_{world_size}"]], g[f"y_{world_size}"])
+    assert err <= 1e-12, err
+
+
+def test_spmd_oracle_used_by_the_reference_arm_matches_golden():
+    """``oracle/parareal_ranks.py`` (timed by ``bench.py --impl reference
+    --gpus N``) reproduces the reference's multi-rank trajectories."""
+    run_distributed(
+        _spmd_oracle_worker, 2, ("parareal_diffusion_2d_multi_iteration",)
+    )
+
+
 def _callable_worker(rank, world_size):
     import oracle
     import pararealml_b200 as ns
