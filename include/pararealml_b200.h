@@ -28,8 +28,10 @@ typedef struct pml_plan_desc {
   int n_dt, n_alg, n_lap; /* equations per LHS kind (differential_equation.py:140-149) */
   int block[3];     /* thread block shape the source was generated for */
   int fused;        /* 1: the source has the fused stage-pair kernels */
-  int fused_block[2]; /* their thread block (contiguous axis, axis 1) */
+  int fused_tile[2]; /* their tile (cells along the contiguous axis, axis 1) */
   int fused_zc;     /* planes of the marching axis per thread block */
+  int fused_threads; /* threads per block (tile + halo 1, rounded to warps) */
+  int fused_smem[2]; /* dynamic shared memory: stage 1+2 / midpoint, stage 3+4 */
   int small_threads; /* > 0: the source has the single-block time loop kernel */
   int zrep;         /* cells along axis 0 per thread in the stage kernels */
 } pml_plan_desc;

@@ -32,8 +32,10 @@ class PlanDesc(Structure):
         ("n_lap", c_int),
         ("block", c_int * 3),
         ("fused", c_int),
-        ("fused_block", c_int * 2),
+        ("fused_tile", c_int * 2),
         ("fused_zc", c_int),
+        ("fused_threads", c_int),
+        ("fused_smem", c_int * 2),
         ("small_threads", c_int),
         ("zrep", c_int),
     ]

@@ -523,17 +523,29 @@ PML_STAGE_KERNEL(pml_stage_rk4_4, PML_RK4_4)
 // ---------------------------------------------------------------------------
 // Fused stage pairs: temporal blocking along the slowest mesh axis.
 //
-// One launch performs two consecutive stages (RK4 1+2, RK4 3+4 or midpoint 1+2).
-// A thread block owns a tile of the in-plane axes plus a one-cell halo ring
-// (PML_FBX x PML_FBY threads <-> halo'd tile cells) and marches along axis 0
-// over PML_FZC planes.  Stage A is evaluated for every cell of the halo'd tile
-// from global memory and its result u_A is written to a 4-slot ring of planes in
-// shared memory; one plane behind, stage B is evaluated for the tile's own cells
-// with all its stencil reads served from that ring.  The intermediate state
-// never goes to HBM: RK4 costs 7 C instead of 17 C doubles of traffic per
-// cell-step at the price of recomputing stage A on the halo ring.
+// One launch performs two consecutive stages (RK4 1+2, RK4 3+4 or midpoint 1+2)
+// so that the intermediate stage state never reaches HBM: RK4 costs 7 C instead
+// of 17 C doubles of traffic per cell-step.
+//
+// A thread block owns a PML_FTX x PML_FTY tile of the in-plane axes and marches
+// along axis 0 over PML_FZC planes.  Per plane ("iteration" i):
+//   * the TMA unit (cp.async.bulk, one row per copy, completion on an mbarrier)
+//     streams the stencil input of stage A (tile + 2 halo cells) into a ring of
+//     shared-memory planes, PML_FDEPTH iterations ahead; for stages 3+4 also
+//     the step-start state and the RK4 accumulator.  No thread ever waits on a
+//     global load, and no registers are tied up by prefetches;
+//   * stage A is evaluated on plane i + 1 for the tile plus ONE halo cell (one
+//     thread per cell) with every stencil operand read from the input ring;
+//     its result goes to a 4-slot ring of shared-memory planes;
+//   * stage B is evaluated on plane i - 1 for the tile's own cells, reading
+//     that ring, and writes the launch's outputs to HBM.  Stage A's increment
+//     and the step-start value of a cell travel from A to B (two iterations
+//     later, same thread) in registers;
+//   * ONE __syncthreads() per iteration: everything an iteration reads was
+//     written in an earlier iteration, so stages A and B are independent
+//     instruction streams the scheduler can interleave.
 // Arithmetic per cell is the same sequence of operations as in the unfused
-// stage kernels above.
+// stage kernels above (bit-identical results).
 // ---------------------------------------------------------------------------
 #if PML_FUSED
 struct PmlFusedArgs {
@@ -543,25 +555,39 @@ struct PmlFusedArgs {
   i64 dir_slot_b;
 };
 
-// in-plane extent of the thread layout (= stage-A cells = tile + halo 1) and of
-// the input ring (tile + halo 2)
+// in-plane geometry: "x" is the contiguous mesh axis, "y" axis 1 of a 3-D mesh
 #if PML_NDIM == 3
-#define PML_MID_PITCH PML_FBX
-#define PML_MID_PLANE (PML_FBX * PML_FBY)
-#define PML_IN_PITCH (PML_FBX + 2)
-#define PML_IN_PLANE ((PML_FBX + 2) * (PML_FBY + 2))
+#define PML_FHY 1
+#define PML_FNX PML_N2
+#define PML_FNY PML_N1
 #else
-#define PML_MID_PITCH 0
-#define PML_MID_PLANE (PML_FBX)
-#define PML_IN_PITCH 0
-#define PML_IN_PLANE (PML_FBX + 2)
+#define PML_FHY 0
+#define PML_FNX PML_N1
+#define PML_FNY 1
 #endif
-#define PML_IN_EXTRA (PML_IN_PLANE - PML_MID_PLANE)
-#define PML_F_THREADS (PML_FBX * PML_FBY)
-#define PML_RING_DOUBLES (4 * PML_C * (PML_IN_PLANE + PML_MID_PLANE))
+#define PML_MW (PML_FTX + 2)              // stage-A tile (halo 1)
+#define PML_MH (PML_FTY + 2 * PML_FHY)
+#define PML_IW (PML_FTX + 4)              // input tile (halo 2)
+#define PML_IH (PML_FTY + 4 * PML_FHY)
+#define PML_MID_PLANE (PML_MW * PML_MH)
+#define PML_IN_PLANE (PML_IW * PML_IH)
+#define PML_YR_PLANE (PML_IW * PML_MH)    // step-start state: rows of stage A
+#define PML_OWN_PLANE (PML_FTX * PML_FTY)
+// components held in the rings: all of them, or only the time-stepped ones when
+// the others are read from the step-start state directly (PML_PASSTHROUGH)
+#define PML_NRING (PML_PASSTHROUGH ? (PML_NDT > 0 ? PML_NDT : 1) : PML_C)
+#define PML_FNS_IN (PML_FDEPTH + 3)       // input ring slots
+#define PML_FNS_P (PML_FDEPTH + 1)        // pointwise ring slots, barriers
 
-// a 4-slot ring of planes in shared memory: base[d + 1] points at this thread's
-// cell in the slot of plane z + d, so a stencil read is base + immediate
+__device__ __forceinline__ constexpr int pml_ring_index(int comp) {
+  if (!PML_PASSTHROUGH) return comp;
+  int n = 0;
+  for (int k = 0; k < comp; ++k) n += PML_KIND[k] == 0;
+  return n;
+}
+
+// a ring of planes in shared memory: base[d + 1] points at this thread's cell
+// in the slot of plane z + d, so a stencil read is base + immediate
 template <int PITCH, int PLANE>
 struct PmlRingSrc {
   const double* base[3];
@@ -574,30 +600,58 @@ struct PmlRingSrc {
       return PML_LD(y + (i64)comp * PML_NCELLS + c.idx + off);
     }
 #if PML_NDIM == 3
-    return base[D0 + 1][comp * PLANE + D1 * PITCH + D2];
+    return base[D0 + 1][pml_ring_index(comp) * PLANE + D1 * PITCH + D2];
 #else
-    return base[D0 + 1][comp * PLANE + D1];
+    return base[D0 + 1][pml_ring_index(comp) * PLANE + D1];
 #endif
   }
 };
 
 enum { PML_F_RK4_12 = 0, PML_F_RK4_34 = 1, PML_F_MID = 2 };
 
-// Dataflow of one thread block (marching index z, ONE barrier per plane):
-//   iteration z:  input plane z+1 (prefetched into registers one iteration
-//                 earlier) -> in_ring slot (z+1)&3; prefetch plane z+2;
-//                 barrier;
-//                 stage A on plane z   (reads in_ring z-1..z+1, writes mid_ring z)
-//                 stage B on plane z-2 (reads mid_ring z-3..z-1, writes HBM)
-// The slot written in an iteration is never one a lagging warp may still read:
-// in_ring (z+1)&3 == (z-3)&3 vs. stage A(z-1) reading z-2..z; mid_ring z&3 ==
-// (z-4)&3 vs. stage B(z-3) reading z-4..z-2 happens before the barrier.
-// No global load sits on the critical path: the input plane, the step-start
-// state (stages 3+4) and the accumulator are all requested one plane ahead
-// into registers; stage A's increment k_A and y travel to stage B (two planes
-// later) in registers.
-#define PML_IN_COMPS (PML_C)
-#define PML_MID_COMPS (PML_C)
+__device__ __forceinline__ unsigned pml_smem_addr(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void pml_mbar_init(unsigned long long* bar,
+                                              unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pml_smem_addr(bar)),
+               "r"(count)
+               : "memory");
+}
+__device__ __forceinline__ void pml_mbar_expect_tx(unsigned long long* bar,
+                                                   unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
+                   pml_smem_addr(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void pml_mbar_wait(unsigned long long* bar,
+                                              unsigned parity) {
+  const unsigned addr = pml_smem_addr(bar);
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n"
+        "  .reg .pred p;\n"
+        "  mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "  selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// one row global -> shared through the TMA unit; completion is signalled on
+// the mbarrier (16-byte aligned addresses, size a multiple of 16 bytes)
+__device__ __forceinline__ void pml_bulk_row(unsigned dst, const double* src,
+                                             unsigned bytes,
+                                             unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1], %2, [%3];" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(pml_smem_addr(bar))
+      : "memory");
+}
 
 // in-plane part of the variant choice (see pml_warp_path): evaluated once per
 // thread block, the marching coordinate only adds a block-uniform condition
@@ -618,63 +672,167 @@ __device__ __forceinline__ int pml_inplane_path(bool active, int i1, int i2) {
 
 template <int MODE>
 __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
-                                               double* smem) {
+                                               double* smem,
+                                               unsigned long long* bars) {
   const PmlArgs& a = f.s;
   constexpr bool first = MODE != PML_F_RK4_34;  // stage A's input is y itself
+  constexpr bool pointwise = MODE == PML_F_RK4_34;  // y and acc rings in use
   constexpr int NK = PML_NDT > 0 ? PML_NDT : 1;
-  constexpr int IN_SLOT = PML_IN_COMPS * PML_IN_PLANE;
-  constexpr int MID_SLOT = PML_MID_COMPS * PML_MID_PLANE;
+  constexpr int IN_SLOT = PML_NRING * PML_IN_PLANE;
+  constexpr int MID_SLOT = PML_NRING * PML_MID_PLANE;
+  constexpr int YR_SLOT = NK * PML_YR_PLANE;
+  constexpr int ACC_SLOT = NK * PML_OWN_PLANE;
   double* in_ring = smem;
-  double* mid_ring = smem + 4 * IN_SLOT;
-  const int tx = threadIdx.x;
+  double* mid_ring = in_ring + PML_FNS_IN * IN_SLOT;
+  double* y_ring = mid_ring + 4 * MID_SLOT;
+  double* acc_ring = y_ring + PML_FNS_P * YR_SLOT;
+  const int tid = threadIdx.x;
+
+  // ---- this thread's cell of the stage-A tile (fixed while marching)
+  const int mr = PML_FHY ? tid / PML_MW : 0;
+  const int mc = PML_FHY ? tid - mr * PML_MW : tid;
+  const int ox = blockIdx.x * PML_FTX;  // mesh coordinates of the tile origin
 #if PML_NDIM == 3
-  const int ty = threadIdx.y;
-  const int tid = ty * PML_FBX + tx;
-  const int o2 = blockIdx.x * (PML_FBX - 2) - 1;  // mesh coords of thread (0,0)
-  const int o1 = blockIdx.y * (PML_FBY - 2) - 1;
-  const int i2 = o2 + tx, i1 = o1 + ty;
-  const bool in_plane = i1 >= 0 && i1 < PML_N1 && i2 >= 0 && i2 < PML_N2;
-  const bool owner = in_plane && tx >= 1 && tx <= PML_FBX - 2 && ty >= 1 &&
-                     ty <= PML_FBY - 2;
-  const int mid_cell = ty * PML_MID_PITCH + tx;
-  const int in_cell = (ty + 1) * PML_IN_PITCH + (tx + 1);
+  const int oy = blockIdx.y * PML_FTY;
   const int chunk = blockIdx.z;
-  // the halo ring of the input tile is loaded by the first PML_IN_EXTRA threads
-  int e1 = 0, e2 = 0;  // in-ring coordinates of this thread's extra cell
-  {
-    const int t = tid;
-    const int row = PML_FBX + 2;
-    if (t < row) { e1 = 0; e2 = t; }
-    else if (t < 2 * row) { e1 = PML_FBY + 1; e2 = t - row; }
-    else if (t < 2 * row + PML_FBY) { e1 = t - 2 * row + 1; e2 = 0; }
-    else { e1 = t - 2 * row - PML_FBY + 1; e2 = PML_FBX + 1; }
-  }
-  const int x1 = o1 - 1 + e1, x2 = o2 - 1 + e2;  // mesh coords of the extra cell
-  const bool has_extra = tid < PML_IN_EXTRA;
-  const bool extra = has_extra && x1 >= 0 && x1 < PML_N1 && x2 >= 0 &&
-                     x2 < PML_N2;
-  const int extra_cell = has_extra ? e1 * PML_IN_PITCH + e2 : 0;
+  const int i1 = oy - 1 + mr, i2 = ox - 1 + mc;
+  const bool in_tile = tid < PML_MID_PLANE;
+  const bool in_plane = in_tile && i1 >= 0 && i1 < PML_N1 && i2 >= 0 && i2 < PML_N2;
+  const bool owner = in_plane && mc >= 1 && mc <= PML_FTX && mr >= 1 && mr <= PML_FTY;
+  const int in_cell = (mr + 1) * PML_IW + (mc + 1);
+  const int own_cell = (mr - 1) * PML_FTX + (mc - 1);
 #else
-  const int tid = tx;
-  const int o1 = blockIdx.x * (PML_FBX - 2) - 1;
-  const int i1 = o1 + tx, i2 = 0;
-  const bool in_plane = i1 >= 0 && i1 < PML_N1;
-  const bool owner = in_plane && tx >= 1 && tx <= PML_FBX - 2;
-  const int mid_cell = tx;
-  const int in_cell = tx + 1;
+  const int oy = 0;
   const int chunk = blockIdx.y;
-  const int e1 = tid == 0 ? 0 : PML_FBX + 1;
-  const int x1 = o1 - 1 + e1, x2 = 0;
-  const bool has_extra = tid < 2;
-  const bool extra = has_extra && x1 >= 0 && x1 < PML_N1;
-  const int extra_cell = has_extra ? e1 : 0;
+  const int i1 = ox - 1 + mc, i2 = 0;
+  const bool in_tile = tid < PML_MID_PLANE;
+  const bool in_plane = in_tile && i1 >= 0 && i1 < PML_N1;
+  const bool owner = in_plane && mc >= 1 && mc <= PML_FTX;
+  const int in_cell = mc + 1;
+  const int own_cell = mc - 1;
 #endif
-  const int z_begin = chunk * PML_FZC;
-  const int z_end = min(z_begin + PML_FZC, PML_N0);
-  // planes: stage B works on [z_begin, z_end), stage A on one more plane on
-  // each side, the input ring on two more
-  const int za_lo = max(z_begin - 1, 0), za_hi = min(z_end, PML_N0 - 1);
-  const int zi_lo = max(z_begin - 2, 0), zi_hi = min(z_end + 1, PML_N0 - 1);
+  const int mid_cell = mr * PML_MW + mc;
+  const int yr_cell = mr * PML_IW + (mc + 1);
+
+  // ---- planes: stage B works on [zb, ze), stage A on one more plane on each
+  // side, the input ring on two more
+  const int zb = chunk * PML_FZC;
+  const int ze = min(zb + PML_FZC, PML_N0);
+  const int a_lo = max(zb - 1, 0), a_hi = min(ze, PML_N0 - 1);
+  const int in_lo = max(zb - 2, 0), in_hi = min(ze + 1, PML_N0 - 1);
+  const int it0 = a_lo - 1, it1 = ze;  // iterations: A(i + 1) and B(i - 1)
+
+  // ---- this thread's TMA row (at most one): rows of the input tile first,
+  // then of the step-start state, then of the accumulator
+  constexpr int N_IN_ROWS = PML_NRING * PML_IH;
+  constexpr int N_Y_ROWS = pointwise ? NK * PML_MH : 0;
+  constexpr int N_ACC_ROWS = pointwise ? NK * PML_FTY : 0;
+  static_assert(N_IN_ROWS + N_Y_ROWS + N_ACC_ROWS <= PML_F_THREADS,
+                "one TMA row per thread");
+  int job = -1;                // 0 input, 1 step-start state, 2 accumulator
+  const double* job_src = nullptr;  // row start in plane 0
+  unsigned job_dst = 0, job_bytes = 0;  // byte offset within a slot
+  unsigned pb_in = 0, pb_y = 0, pb_acc = 0;  // bytes per plane of each ring
+  {
+    // x range of the wide rows (input, step-start state) and the tile rows
+    const int wx0 = max(ox - 2, 0), wx1 = min(ox + PML_FTX + 2, PML_FNX);
+    const int tx0 = ox, tx1 = min(ox + PML_FTX, PML_FNX);
+    auto rows_in = [&](int r0, int n) {  // rows of [r0, r0 + n) inside the mesh
+      return max(0, min(r0 + n, PML_FNY) - max(r0, 0));
+    };
+    pb_in = (unsigned)(PML_NRING * rows_in(oy - 2 * PML_FHY, PML_IH) *
+                                (wx1 - wx0) * 8);
+    if (pointwise) {
+      pb_y = (unsigned)(NK * rows_in(oy - PML_FHY, PML_MH) *
+                                  (wx1 - wx0) * 8);
+      pb_acc = (unsigned)(NK * rows_in(oy, PML_FTY) * (tx1 - tx0) * 8);
+    }
+    int q = tid;
+    if (q < N_IN_ROWS) {
+      const int rc = q / PML_IH, r = q - rc * PML_IH;  // ring component, row
+      const int row = oy - 2 * PML_FHY + r;
+      int comp = 0;  // component held at ring index rc
+#pragma unroll
+      for (int k = 0; k < PML_C; ++k)
+        if ((!PML_PASSTHROUGH || PML_KIND[k] == 0) && pml_ring_index(k) == rc)
+          comp = k;
+      if (row >= 0 && row < PML_FNY) {
+        job = 0;
+        const double* base =
+            (first || (PML_PASSTHROUGH && PML_KIND[comp] != 0)) ? a.y : a.u;
+        job_src = base + (i64)comp * PML_NCELLS + (i64)row * PML_FNX + wx0;
+        job_dst = (unsigned)(((rc * PML_IH + r) * PML_IW + (wx0 - (ox - 2))) * 8);
+        job_bytes = (unsigned)((wx1 - wx0) * 8);
+      }
+    } else if (pointwise && (q -= N_IN_ROWS) < N_Y_ROWS) {
+      const int j = q / PML_MH, r = q - j * PML_MH;
+      const int row = oy - PML_FHY + r;
+      if (row >= 0 && row < PML_FNY) {
+        job = 1;
+        job_src = a.y + (i64)PML_DT_IDX[j] * PML_NCELLS + (i64)row * PML_FNX + wx0;
+        job_dst = (unsigned)(((j * PML_MH + r) * PML_IW + (wx0 - (ox - 2))) * 8);
+        job_bytes = (unsigned)((wx1 - wx0) * 8);
+      }
+    } else if (pointwise && (q -= N_Y_ROWS) < N_ACC_ROWS) {
+      const int j = q / PML_FTY, r = q - j * PML_FTY;
+      const int row = oy + r;
+      if (row < PML_FNY) {
+        job = 2;
+        job_src = a.acc_in + (i64)PML_DT_IDX[j] * PML_NCELLS + (i64)row * PML_FNX + tx0;
+        job_dst = (unsigned)(((j * PML_FTY + r) * PML_FTX) * 8);
+        job_bytes = (unsigned)((tx1 - tx0) * 8);
+      }
+    }
+  }
+  const unsigned in_ring_s = pml_smem_addr(in_ring);
+  const unsigned y_ring_s = pml_smem_addr(y_ring);
+  const unsigned acc_ring_s = pml_smem_addr(acc_ring);
+
+  // everything iteration j reads for the first time: input plane j + 2,
+  // step-start plane j + 1 (stage A), accumulator plane j - 1 (stage B)
+  auto fetch = [&](int j, int in_first) {
+    unsigned long long* bar = bars + (j - it0) % PML_FNS_P;
+    if (tid == 0) {
+      unsigned tx = 0;
+      for (int p = in_first; p <= j + 2; ++p)
+        if (p >= in_lo && p <= in_hi) tx += pb_in;
+      if (pointwise) {
+        if (j + 1 >= a_lo && j + 1 <= a_hi) tx += pb_y;
+        if (j - 1 >= zb && j - 1 < ze) tx += pb_acc;
+      }
+      pml_mbar_expect_tx(bar, tx);
+    }
+    if (job == 0) {
+      for (int p = in_first; p <= j + 2; ++p)
+        if (p >= in_lo && p <= in_hi)
+          pml_bulk_row(in_ring_s + (unsigned)((p + PML_FNS_IN) % PML_FNS_IN) *
+                                       (IN_SLOT * 8) + job_dst,
+                       job_src + (i64)p * PmlAx<0>::S, job_bytes, bar);
+    } else if (job == 1) {
+      const int p = j + 1;
+      if (p >= a_lo && p <= a_hi)
+        pml_bulk_row(y_ring_s + (unsigned)((p + PML_FNS_P) % PML_FNS_P) *
+                                    (YR_SLOT * 8) + job_dst,
+                     job_src + (i64)p * PmlAx<0>::S, job_bytes, bar);
+    } else if (job == 2) {
+      const int p = j - 1;
+      if (p >= zb && p < ze)
+        pml_bulk_row(acc_ring_s + (unsigned)((p + PML_FNS_P) % PML_FNS_P) *
+                                      (ACC_SLOT * 8) + job_dst,
+                     job_src + (i64)p * PmlAx<0>::S, job_bytes, bar);
+    }
+  };
+
+  if (tid == 0) {
+#pragma unroll
+    for (int k = 0; k < PML_FNS_P; ++k) pml_mbar_init(bars + k, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // prologue: the first iteration needs three input planes at once
+  fetch(it0, it0);
+#pragma unroll 1
+  for (int j = it0 + 1; j < it0 + PML_FDEPTH; ++j) fetch(j, j + 2);
 
   PmlArgs b = a;  // stage B sees its own time and table slots
   b.t_eval = f.t_eval_b;
@@ -685,111 +843,48 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
   const int path_a_in = pml_inplane_path(in_plane, i1, i2);
   const int path_b_in = pml_inplane_path(owner, i1, i2);
 
-  // stage A's stencil input: y (first stages) or the previous stage's output
-  const double* IN[PML_C];
-#pragma unroll
-  for (int k = 0; k < PML_C; ++k)
-    IN[k] = ((first || (PML_PASSTHROUGH && PML_KIND[k] != 0)) ? a.y : a.u) +
-            (i64)k * PML_NCELLS;
-  const i64 own_off = pml_lin(0, in_plane ? i1 : 0, in_plane ? i2 : 0);
-  const i64 extra_off = pml_lin(0, extra ? x1 : 0, extra ? x2 : 0);
-
-  // prefetch registers: one input plane (own + extra cell), the step-start
-  // state for stages 3+4 and the accumulator stage B will need
-  double pre_own[PML_C], pre_extra[PML_C], pre_y[NK], acc_cur[NK];
-#pragma unroll
-  for (int j = 0; j < NK; ++j) pre_y[j] = acc_cur[j] = 0.0;
-  auto prefetch = [&](int zp) {
-    const bool valid = zp >= zi_lo && zp <= zi_hi;
-    const i64 zoff = (i64)zp * PmlAx<0>::S;
-#pragma unroll
-    for (int k = 0; k < PML_C; ++k) {
-      const bool ring_comp = !(PML_PASSTHROUGH && PML_KIND[k] != 0);
-      pre_own[k] = (ring_comp && valid && in_plane)
-                       ? PML_LD(IN[k] + zoff + own_off) : 0.0;
-      pre_extra[k] = (ring_comp && valid && extra)
-                         ? PML_LD(IN[k] + zoff + extra_off) : 0.0;
-    }
-  };
-  // step-start state at this thread's stage-A cell of plane zp (stages 3+4)
-  auto prefetch_y = [&](int zp, double* dst) {
-    const bool valid = zp >= za_lo && zp <= za_hi && in_plane;
-    const i64 zoff = (i64)zp * PmlAx<0>::S;
-#pragma unroll
-    for (int j = 0; j < PML_NDT; ++j)
-      dst[j] = valid ? PML_LD(a.y + (i64)PML_DT_IDX[j] * PML_NCELLS + zoff +
-                              own_off)
-                     : 0.0;
-  };
-  auto deposit = [&](int zp) {
-    double* slot = in_ring + ((zp & 3) * IN_SLOT);
-#pragma unroll
-    for (int k = 0; k < PML_C; ++k) {
-      if (PML_PASSTHROUGH && PML_KIND[k] != 0) continue;
-      slot[k * PML_IN_PLANE + in_cell] = pre_own[k];
-      if (has_extra) slot[k * PML_IN_PLANE + extra_cell] = pre_extra[k];
-    }
-  };
-
-  // prologue: planes zi_lo .. za_lo into the ring, za_lo + 1 into registers
-  for (int zp = zi_lo; zp <= za_lo; ++zp) {
-    prefetch(zp);
-    deposit(zp);
-  }
-  prefetch(za_lo + 1);
-  if (!first) prefetch_y(za_lo, pre_y);
-
-  // stage-A results stage B needs two planes later
+  // stage-A results stage B needs two iterations later
   double ka_1[NK], y_1[NK], ka_2[NK], y_2[NK];
 #pragma unroll
   for (int j = 0; j < NK; ++j) ka_1[j] = y_1[j] = ka_2[j] = y_2[j] = 0.0;
 
-  i64 idx_a = pml_lin(za_lo, in_plane ? i1 : 0, in_plane ? i2 : 0);
-  for (int z = za_lo; z <= z_end + 1; ++z, idx_a += PmlAx<0>::S) {
-    deposit(z + 1);   // plane z + 1 was prefetched during the last iteration
-    prefetch(z + 2);  // consumed in the next iteration
-    const int zz = z - 2;  // stage B's plane
-    const bool b_plane = zz >= z_begin && zz < z_end;
-    const i64 idx_b = idx_a - 2 * PmlAx<0>::S;
-    double acc_next[NK], y_next_plane[NK], ka_new[NK], y_new[NK];
+  const i64 idx0 = pml_lin(0, in_plane ? i1 : 0, in_plane ? i2 : 0);
+#pragma unroll 1
+  for (int i = it0; i <= it1; ++i) {
+    // the slots freed by the barrier that ended iteration i - 1 are refilled
+    if (i + PML_FDEPTH <= it1) fetch(i + PML_FDEPTH, i + PML_FDEPTH + 2);
+    pml_mbar_wait(bars + (i - it0) % PML_FNS_P,
+                  (unsigned)(((i - it0) / PML_FNS_P) & 1));
+    double ka_new[NK], y_new[NK];
 #pragma unroll
-    for (int j = 0; j < NK; ++j)
-      acc_next[j] = y_next_plane[j] = ka_new[j] = y_new[j] = 0.0;
-    if (!first) prefetch_y(z + 1, y_next_plane);
-    if (MODE == PML_F_RK4_34) {
-      // the accumulator stage B needs in the NEXT iteration (plane z - 1)
-      const bool need = owner && (zz + 1) >= z_begin && (zz + 1) < z_end;
-#pragma unroll
-      for (int j = 0; j < PML_NDT; ++j)
-        acc_next[j] =
-            need ? PML_LD_ONCE(a.acc_in + (i64)PML_DT_IDX[j] * PML_NCELLS +
-                               idx_b + PmlAx<0>::S)
-                 : 0.0;
-    }
-    __syncthreads();
-    // ---- stage A on plane z (halo'd tile), stencil reads from the input ring
+    for (int j = 0; j < NK; ++j) ka_new[j] = y_new[j] = 0.0;
+    // ---- stage A on plane i + 1 (tile + halo 1), operands from the input ring
     {
-      const bool a_plane = z >= za_lo && z <= za_hi;
-      const bool active = in_plane && a_plane;
+      const int z = i + 1;
+      const bool active = in_plane && z >= a_lo && z <= a_hi;
       const int path = (z > 0 && z < PML_N0 - 1) ? path_a_in : 0;
       if (active) {
         PmlCell c;
         c.i0 = z;
         c.i1 = i1;
         c.i2 = i2;
-        c.idx = idx_a;
-        PmlRingSrc<PML_IN_PITCH, PML_IN_PLANE> src;
+        c.idx = idx0 + (i64)z * PmlAx<0>::S;
+        PmlRingSrc<PML_IW, PML_IN_PLANE> src;
         src.y = a.y;
 #pragma unroll
         for (int d = -1; d <= 1; ++d)
-          src.base[d + 1] = in_ring + (((z + d) & 3) * IN_SLOT) + in_cell;
+          src.base[d + 1] =
+              in_ring + ((z + d + PML_FNS_IN) % PML_FNS_IN) * IN_SLOT + in_cell;
         double K[NK];
         pml_eval_dt(path, a, src, c, a.t_eval, K);
         double* slot = mid_ring + ((z & 3) * MID_SLOT) + mid_cell;
+        const double* yr =
+            y_ring + ((z + PML_FNS_P) % PML_FNS_P) * YR_SLOT + yr_cell;
 #pragma unroll
         for (int j = 0; j < PML_NDT; ++j) {
           const int k = PML_DT_IDX[j];
-          const double y0 = first ? src.template rel<0, 0, 0>(k, c) : pre_y[j];
+          const double y0 = first ? src.template rel<0, 0, 0>(k, c)
+                                  : yr[j * PML_YR_PLANE];
           double ua, ka = 0.0;
           if (MODE == PML_F_MID) {
             ua = y0 + (a.dt / 2.0) * K[j];
@@ -797,7 +892,8 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
             ka = a.dt * K[j];
             ua = MODE == PML_F_RK4_12 ? y0 + ka / 2.0 : y0 + ka;
           }
-          slot[k * PML_MID_PLANE] = pml_dirichlet(a, a.dir_slot, k, c, ua);
+          slot[pml_ring_index(k) * PML_MID_PLANE] =
+              pml_dirichlet(a, a.dir_slot, k, c, ua);
           ka_new[j] = ka;
           y_new[j] = y0;
         }
@@ -810,28 +906,31 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
                 a, a.dir_slot, k, c, PML_LD(a.y + (i64)k * PML_NCELLS + c.idx));
           }
         }
-        if (first && owner && z >= z_begin && z < z_end)
+        if (first && owner && z >= zb && z < ze)
           pml_first_stage_extras(path, a, src, c);
 #endif
       }
     }
-    // ---- stage B on plane z - 2 (tile cells), stencil reads from the mid ring
+    // ---- stage B on plane i - 1 (tile cells), operands from the stage-A ring
     {
-      const bool active = owner && b_plane;
-      const int path = (zz > 0 && zz < PML_N0 - 1) ? path_b_in : 0;
+      const int z = i - 1;
+      const bool active = owner && z >= zb && z < ze;
+      const int path = (z > 0 && z < PML_N0 - 1) ? path_b_in : 0;
       if (active) {
         PmlCell c;
-        c.i0 = zz;
+        c.i0 = z;
         c.i1 = i1;
         c.i2 = i2;
-        c.idx = idx_b;
-        PmlRingSrc<PML_MID_PITCH, PML_MID_PLANE> src;
+        c.idx = idx0 + (i64)z * PmlAx<0>::S;
+        PmlRingSrc<PML_MW, PML_MID_PLANE> src;
         src.y = a.y;
 #pragma unroll
         for (int d = -1; d <= 1; ++d)
-          src.base[d + 1] = mid_ring + (((zz + d) & 3) * MID_SLOT) + mid_cell;
+          src.base[d + 1] = mid_ring + (((z + d) & 3) * MID_SLOT) + mid_cell;
         double K[NK];
         pml_eval_dt(path, b, src, c, b.t_eval, K);
+        const double* ar =
+            acc_ring + ((z + PML_FNS_P) % PML_FNS_P) * ACC_SLOT + own_cell;
 #pragma unroll
         for (int j = 0; j < PML_NDT; ++j) {
           const int k = PML_DT_IDX[j];
@@ -844,7 +943,7 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
                    pml_dirichlet(b, b.dir_slot, k, c, y0 + kk / 2.0));
           } else if (MODE == PML_F_RK4_34) {
             const double kk = b.dt * K[j];
-            const double acc = acc_cur[j] + 2.0 * ka;
+            const double acc = ar[j * PML_OWN_PLANE] + 2.0 * ka;
             PML_ST(b.y_next + o,
                    pml_dirichlet(b, b.dir_slot, k, c, y0 + pml_div6(acc + kk)));
           } else {
@@ -866,21 +965,21 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
     }
 #pragma unroll
     for (int j = 0; j < NK; ++j) {
-      acc_cur[j] = acc_next[j];
-      pre_y[j] = y_next_plane[j];
       ka_2[j] = ka_1[j];
       y_2[j] = y_1[j];
       ka_1[j] = ka_new[j];
       y_1[j] = y_new[j];
     }
+    __syncthreads();
   }
 }
 
-#define PML_FUSED_KERNEL(NAME, MODE)                                           \
-  extern "C" __global__ void __launch_bounds__(PML_FBX* PML_FBY, PML_FMIN_BLOCKS) \
-      NAME(const __grid_constant__ PmlFusedArgs f) {                          \
-    extern __shared__ double pml_ring[];                                       \
-    pml_fused_body<MODE>(f, pml_ring);                                         \
+#define PML_FUSED_KERNEL(NAME, MODE)                                         \
+  extern "C" __global__ void __launch_bounds__(PML_F_THREADS, PML_FMIN_BLOCKS) \
+      NAME(const __grid_constant__ PmlFusedArgs f) {                        \
+    extern __shared__ __align__(128) double pml_ring[];                      \
+    __shared__ unsigned long long pml_bars[PML_FNS_P];                       \
+    pml_fused_body<MODE>(f, pml_ring, pml_bars);                             \
   }
 
 PML_FUSED_KERNEL(pml_fused_rk4_12, PML_F_RK4_12)

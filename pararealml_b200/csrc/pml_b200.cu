@@ -16,6 +16,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdint>
 #include <cstring>
 #include <fstream>
 #include <string>
@@ -195,7 +196,7 @@ struct pml_plan {
   CUfunction stage[7] = {};
   CUfunction fused[3] = {};  // rk4 1+2, rk4 3+4, midpoint 1+2
   dim3 fgrid, fblock;
-  unsigned fsmem = 0;
+  unsigned fsmem[3] = {0, 0, 0};
   CUfunction small_run = nullptr;
   CUfunction eval_rhs = nullptr;
   CUfunction jac_init = nullptr, jac_sweep = nullptr, jac_check = nullptr,
@@ -345,21 +346,17 @@ int pml_plan_create(const char* source, const pml_plan_desc* desc,
   if (desc->fused) {
     static const char* fnames[3] = {"pml_fused_rk4_12", "pml_fused_rk4_34",
                                     "pml_fused_mid"};
-    const int fbx = desc->fused_block[0], fby = desc->fused_block[1];
-    const unsigned mid_plane = (unsigned)(fbx * fby);
-    const unsigned in_plane = desc->n_dims == 3
-                                  ? (unsigned)((fbx + 2) * (fby + 2))
-                                  : (unsigned)(fbx + 2);
-    // 4 slots of y_dim planes in each of the two rings
-    const unsigned in_comps = (unsigned)desc->y_dim;
-    const unsigned mid_comps = (unsigned)desc->y_dim;
-    p->fsmem = 4u * (in_comps * in_plane + mid_comps * mid_plane) * 8u;
+    // rk4 1+2 and midpoint read only the input ring; rk4 3+4 adds the rings
+    // of the step-start state and the accumulator
+    p->fsmem[0] = (unsigned)desc->fused_smem[0];
+    p->fsmem[1] = (unsigned)desc->fused_smem[1];
+    p->fsmem[2] = (unsigned)desc->fused_smem[0];
     for (int i = 0; i < 3; ++i) {
       r = g_drv.moduleGetFunction(&p->fused[i], p->module, fnames[i]);
-      if (r == CUDA_SUCCESS && p->fsmem > 48 * 1024)
+      if (r == CUDA_SUCCESS && p->fsmem[i] > 48 * 1024)
         r = g_drv.funcSetAttribute(
             p->fused[i], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
-            (int)p->fsmem);
+            (int)p->fsmem[i]);
       if (r == CUDA_SUCCESS)
         r = g_drv.funcSetAttribute(
             p->fused[i], CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT,
@@ -372,13 +369,14 @@ int pml_plan_create(const char* source, const pml_plan_desc* desc,
       }
     }
     auto cdivf = [](int a, int d) { return (unsigned)((a + d - 1) / d); };
-    p->fblock = dim3(fbx, fby, 1);
+    p->fblock = dim3((unsigned)desc->fused_threads, 1, 1);
     const int* n = desc->shape;
+    const int ftx = desc->fused_tile[0], fty = desc->fused_tile[1];
     if (desc->n_dims == 3)
-      p->fgrid = dim3(cdivf(n[2], fbx - 2), cdivf(n[1], fby - 2),
+      p->fgrid = dim3(cdivf(n[2], ftx), cdivf(n[1], fty),
                       cdivf(n[0], desc->fused_zc));
     else
-      p->fgrid = dim3(cdivf(n[1], fbx - 2), cdivf(n[0], desc->fused_zc), 1);
+      p->fgrid = dim3(cdivf(n[1], ftx), cdivf(n[0], desc->fused_zc), 1);
   }
   if (desc->small_threads > 0) {
     r = g_drv.moduleGetFunction(&p->small_run, p->module, "pml_small_run");
@@ -531,17 +529,21 @@ int pml_fdm_run(pml_plan* p, int integrator, const pml_workspace* ws,
       void* fparams[] = {&f};
       CUresult r_ = g_drv.launchKernel(p->fused[k], p->fgrid.x, p->fgrid.y,
                                        p->fgrid.z, p->fblock.x, p->fblock.y, 1,
-                                       p->fsmem, s, fparams, nullptr);
+                                       p->fsmem[k], s, fparams, nullptr);
       if (r_ != CUDA_SUCCESS) return fail("fused launch: " + cu_err(r_));
       p->launches += 1;
       return 0;
     };
     int rc = 0;
+    // the fused kernels move rows with the TMA unit: 16-byte aligned planes
+    auto aligned = [](const void* q) { return ((uintptr_t)q & 15u) == 0; };
+    const bool use_fused = p->desc.fused && aligned(y) && aligned(y_next) &&
+                           aligned(ws->u_b) && aligned(ws->acc);
     if (integrator == PML_INTEGRATOR_FORWARD_EULER) {
       rc = stage(0, y, nullptr, t, s_t, s_f);
-    } else if (p->desc.fused && integrator == PML_INTEGRATOR_EXPLICIT_MIDPOINT) {
+    } else if (use_fused && integrator == PML_INTEGRATOR_EXPLICIT_MIDPOINT) {
       rc = fused(2, y, nullptr, t, s_t, s_h, t + half, s_h, s_f);
-    } else if (p->desc.fused) {
+    } else if (use_fused) {
       // RK4: stages 1+2 write u_b (= u3) and acc; stages 3+4 write the slot
       rc = fused(0, y, ws->u_b, t, s_t, s_h, t + half, s_h, s_h);
       if (!rc) rc = fused(1, ws->u_b, nullptr, t + half, s_h, s_f, t + d_t, s_f, s_f);

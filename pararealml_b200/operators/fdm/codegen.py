@@ -86,9 +86,8 @@ class ProblemSpec:
     coherent_loads: bool = False
     eval_only: bool = False  # the differentiator entry points
     block: Optional[Tuple[int, int, int]] = None
-    #: (threads along the contiguous axis, threads along axis 1, planes per
-    #: chunk) of the fused stage-pair kernels, or None to generate none
-    fused: Optional[Tuple[int, int, int]] = None
+    #: tile of the fused stage-pair kernels, or None to generate none
+    fused: Optional["FusedTile"] = None
     #: threads of the single-block time-loop kernel for small meshes (0: none)
     small_threads: int = 0
     #: cells along axis 0 every thread of a stage kernel walks
@@ -130,42 +129,88 @@ def default_small(shape) -> int:
     return int(min(1024, max(32, 32 * -(-cells // 32))))
 
 
-def default_fused(shape, y_dim, n_dt=None) -> Optional[Tuple[int, int, int]]:
-    """Tile of the fused stage-pair kernels (csrc/fdm_template.cuh): threads
-    cover the tile plus a one-cell halo ring; planes per chunk are chosen so
-    that the grid has several waves of thread blocks."""
-    # opt-in: on B200 the fused pair kernels are correct but (round 1) still
-    # slower than four unfused stage launches, see DESIGN.md section 3
-    if os.environ.get("PML_FUSE", "0") != "1":
+@dataclass(frozen=True)
+class FusedTile:
+    """Geometry of the fused stage-pair kernels (csrc/fdm_template.cuh)."""
+
+    tx: int  # tile cells along the contiguous mesh axis
+    ty: int  # tile cells along axis 1 (3-D meshes; 1 otherwise)
+    zc: int  # planes of the marching axis per thread block
+    depth: int  # iterations the TMA copies run ahead
+    threads: int  # one thread per cell of the tile + halo 1
+    smem_first: int  # dynamic shared memory of the stage 1+2 / midpoint kernels
+    smem_pointwise: int  # ... of the stage 3+4 kernel (adds y and acc rings)
+    min_blocks: int
+
+
+SMEM_PER_BLOCK_MAX = 227 * 1024
+SMEM_PER_SM = 228 * 1024
+
+
+def default_fused(shape, y_dim, n_dt=None, passthrough=False) -> Optional[FusedTile]:
+    """Tile of the fused stage-pair kernels: the stage-A tile (tile + halo 1)
+    has one thread per cell, rows are moved by the TMA unit and therefore have
+    to start on 16-byte boundaries (even extent of the contiguous axis)."""
+    mode = os.environ.get("PML_FUSE", "0")
+    if mode != "1":
         return None
     nd = len(shape)
-    if nd < 2 or any(n < 3 for n in shape):
-        return None
-    if os.environ.get("PML_FBLOCK"):
-        fbx, fby = (int(v) for v in os.environ["PML_FBLOCK"].split(","))
-    elif nd == 3:
-        fbx, fby = 32, 8
-    else:
-        fbx, fby = 128, 1
-    if nd == 2:
-        fby = 1
-    last = shape[-1]
-    fbx = max(32, min(fbx, 32 * -(-(last + 2) // 32)))
-    in_plane = (fbx + 2) * (fby + 2) if nd == 3 else fbx + 2
     n_dt = y_dim if n_dt is None else n_dt
-    smem = 4 * 8 * y_dim * (in_plane + fbx * fby)
-    if smem > 200 * 1024:
+    if nd < 2 or any(n < 3 for n in shape) or n_dt < 1 or shape[-1] % 2:
         return None
-    tiles = -(-last // (fbx - 2))
+    if os.environ.get("PML_FTILE"):
+        tx, ty = (int(v) for v in os.environ["PML_FTILE"].split(","))
+    elif nd == 3:
+        tx, ty = 32, 16
+    else:
+        tx, ty = 254, 1
+    if nd == 2:
+        ty = 1
+    tx = max(2, min(tx, shape[-1] + (shape[-1] % 2)))
+    tx -= tx % 2
     if nd == 3:
-        tiles *= -(-shape[1] // (fby - 2))
+        ty = max(1, min(ty, shape[1]))
+    depth = int(os.environ.get("PML_FDEPTH", "2"))
+    n_ring = n_dt if passthrough else y_dim
+    hy = 1 if nd == 3 else 0
+
+    def geometry(tx, ty, depth):
+        mw, mh = tx + 2, ty + 2 * hy
+        iw, ih = tx + 4, ty + 4 * hy
+        threads = 32 * -(-(mw * mh) // 32)
+        first = 8 * ((depth + 3) * n_ring * iw * ih + 4 * n_ring * mw * mh)
+        pointwise = first + 8 * (depth + 1) * n_dt * (iw * mh + tx * ty)
+        rows = n_ring * ih + n_dt * mh + n_dt * ty
+        return threads, first, pointwise, rows
+
+    while True:
+        threads, first, pointwise, rows = geometry(tx, ty, depth)
+        if threads <= 1024 and rows <= threads and pointwise + 2048 <= SMEM_PER_BLOCK_MAX:
+            break
+        if depth > 1:
+            depth -= 1
+        elif nd == 3 and ty > 2:
+            ty //= 2
+        elif tx > 8:
+            tx = (tx // 2) - ((tx // 2) % 2)
+        else:
+            return None
+    tiles = -(-shape[-1] // tx) * (-(-shape[1] // ty) if nd == 3 else 1)
     if os.environ.get("PML_FZC"):
         zc = int(os.environ["PML_FZC"])
     else:
-        chunks = max(1, -(-(8 * N_SMS) // tiles))
-        zc = max(16, -(-shape[0] // chunks))
-    zc = min(zc, shape[0])
-    return (fbx, fby, zc)
+        # enough thread blocks for ~8 waves, at least 32 planes per block so
+        # that the two extra planes a chunk recomputes stay cheap
+        per_sm = max(1, min(SMEM_PER_SM // (pointwise + 1024), 2048 // threads))
+        chunks = max(1, -(-(8 * N_SMS * per_sm) // tiles))
+        zc = max(32, -(-shape[0] // chunks))
+    zc = max(1, min(zc, shape[0]))
+    # resident blocks per SM by shared memory and threads, capped so that the
+    # compiler keeps ~96 registers per thread (rotating stage-A results)
+    per_sm = max(1, min(SMEM_PER_SM // (pointwise + 1024), 2048 // threads,
+                        65536 // (96 * threads)))
+    min_blocks = int(os.environ.get("PML_FMIN_BLOCKS", str(per_sm)))
+    return FusedTile(tx, ty, zc, depth, threads, first, pointwise, min_blocks)
 
 
 class _LeafBuilder:
@@ -488,11 +533,6 @@ def generate_source(spec: ProblemSpec) -> str:
         os.environ.get("PML_MIN_BLOCKS", str(max(1, 1024 // threads)))
     )
     fused = spec.fused
-    if fused is not None:
-        fthreads = fused[0] * fused[1]
-        fmin = int(
-            os.environ.get("PML_FMIN_BLOCKS", str(max(1, 1024 // fthreads)))
-        )
     lines = [
         "// generated by pararealml_b200/operators/fdm/codegen.py",
         f"#define PML_NDIM {nd}",
@@ -513,10 +553,12 @@ def generate_source(spec: ProblemSpec) -> str:
         f"#define PML_STREAMING {int(os.environ.get('PML_STREAM', '0'))}",
         f"#define PML_MIN_BLOCKS {min_blocks}",
         f"#define PML_FUSED {int(fused is not None)}",
-        f"#define PML_FBX {fused[0] if fused else 32}",
-        f"#define PML_FBY {fused[1] if fused else 1}",
-        f"#define PML_FZC {fused[2] if fused else 1}",
-        f"#define PML_FMIN_BLOCKS {fmin if fused else 1}",
+        f"#define PML_FTX {fused.tx if fused else 32}",
+        f"#define PML_FTY {fused.ty if fused else 1}",
+        f"#define PML_FZC {fused.zc if fused else 1}",
+        f"#define PML_FDEPTH {fused.depth if fused else 1}",
+        f"#define PML_F_THREADS {fused.threads if fused else 32}",
+        f"#define PML_FMIN_BLOCKS {fused.min_blocks if fused else 1}",
         f"#define PML_ZREP {max(1, int(spec.zrep))}",
         f"#define PML_BX {block[0]}",
         f"#define PML_BY {block[1]}",

@@ -79,8 +79,11 @@ class DevicePlan:
         fused = spec.fused
         desc.fused = int(fused is not None)
         if fused is not None:
-            desc.fused_block[0], desc.fused_block[1] = fused[0], fused[1]
-            desc.fused_zc = fused[2]
+            desc.fused_tile[0], desc.fused_tile[1] = fused.tx, fused.ty
+            desc.fused_zc = fused.zc
+            desc.fused_threads = fused.threads
+            desc.fused_smem[0] = fused.smem_first
+            desc.fused_smem[1] = fused.smem_pointwise
         self.fused = fused
         desc.small_threads = int(spec.small_threads)
         desc.zrep = max(1, int(spec.zrep))

@@ -74,7 +74,8 @@ def plan_overrides(cp, low: LoweredProblem, y0: Optional[np.ndarray]) -> dict:
     return {
         "passthrough": passthrough,
         "fused": codegen.default_fused(
-            low.shape, low.y_dim, len(low.kind_indices("D_Y_OVER_D_T"))
+            low.shape, low.y_dim, len(low.kind_indices("D_Y_OVER_D_T")),
+            passthrough,
         ),
         "small_threads": codegen.default_small(low.shape),
         "zrep": codegen.default_zrep(low.shape),
