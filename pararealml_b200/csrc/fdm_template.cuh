@@ -48,13 +48,11 @@ struct PmlArgs {
   double* lap_rhs;        // right-hand sides of the Y_LAPLACIAN equations
   double t_eval;          // time the right-hand side is evaluated at
   double dt;
-  i64 neu_slot;           // boundary table slots (dynamic conditions)
-  i64 dir_slot;           // Dirichlet slot of this stage's output
-  i64 dir_slot_full;      // Dirichlet slot of t + dt (algebraic equations)
-  const double* neu[6];   // Neumann tables per face (axis * 2 + side)
-  i64 neu_stride[6];      // doubles per slot (0 = static)
-  const double* dir[6];   // Dirichlet tables per face
-  i64 dir_stride[6];
+  // boundary tables per face (axis * 2 + side), already offset by the host to
+  // the time slot they are needed at (dynamic conditions)
+  const double* neu[6];       // Neumann values at the evaluation time
+  const double* dir[6];       // Dirichlet values of this stage's output time
+  const double* dir_full[6];  // Dirichlet values of t + dt (algebraic equations)
   const double* coord[3];  // vertex coordinates along each axis
   const double* aux[4];    // 1/r[i0], sin(phi)[i2], cos(phi)[i2], 1/sin(phi)[i2]
 };
@@ -119,8 +117,7 @@ __device__ __forceinline__ double pml_neu(const PmlArgs& a, int comp, int i0,
                                           int i1, int i2) {
   constexpr int f = A * 2 + SIDE;
   if (!((PML_NEU_MASK >> f) & 1)) return PML_NAN;
-  return __ldg(a.neu[f] + a.neu_slot * a.neu_stride[f] +
-               pml_face<A>(i0, i1, i2) * PML_C + comp);
+  return __ldg(a.neu[f] + pml_face<A>(i0, i1, i2) * PML_C + comp);
 }
 
 // ---------------------------------------------------------------------------
@@ -258,33 +255,31 @@ __device__ __forceinline__ double pml_d2m_at(const PmlArgs& a, const SRC& s,
 // Dirichlet overwrite: faces in the order axis 0 lower, axis 0 upper, axis 1
 // lower, ... so later faces win on shared edges (constrained_problem.py:286-295)
 template <int A>
-__device__ __forceinline__ double pml_dirichlet_axis(const PmlArgs& a, i64 slot,
+__device__ __forceinline__ double pml_dirichlet_axis(const double* const* dir,
                                                      int comp, int i0, int i1,
                                                      int i2, double v) {
   typedef PmlAx<A> X;
   const int ia = pml_ia<A>(i0, i1, i2);
   if (((PML_DIR_MASK >> (A * 2)) & 1) && ia == 0) {
     constexpr int f = A * 2;
-    const double t = __ldg(a.dir[f] + slot * a.dir_stride[f] +
-                           pml_face<A>(i0, i1, i2) * PML_C + comp);
+    const double t = __ldg(dir[f] + pml_face<A>(i0, i1, i2) * PML_C + comp);
     if (t == t) v = t;
   }
   if (((PML_DIR_MASK >> (A * 2 + 1)) & 1) && ia == X::N - 1) {
     constexpr int f = A * 2 + 1;
-    const double t = __ldg(a.dir[f] + slot * a.dir_stride[f] +
-                           pml_face<A>(i0, i1, i2) * PML_C + comp);
+    const double t = __ldg(dir[f] + pml_face<A>(i0, i1, i2) * PML_C + comp);
     if (t == t) v = t;
   }
   return v;
 }
 
-__device__ __forceinline__ double pml_dirichlet(const PmlArgs& a, i64 slot,
+__device__ __forceinline__ double pml_dirichlet(const double* const* dir,
                                                 int comp, const PmlCell& c,
                                                 double v) {
 #if PML_DIR_MASK != 0
-  if (PML_NDIM >= 1) v = pml_dirichlet_axis<0>(a, slot, comp, c.i0, c.i1, c.i2, v);
-  if (PML_NDIM >= 2) v = pml_dirichlet_axis<1>(a, slot, comp, c.i0, c.i1, c.i2, v);
-  if (PML_NDIM >= 3) v = pml_dirichlet_axis<2>(a, slot, comp, c.i0, c.i1, c.i2, v);
+  if (PML_NDIM >= 1) v = pml_dirichlet_axis<0>(dir, comp, c.i0, c.i1, c.i2, v);
+  if (PML_NDIM >= 2) v = pml_dirichlet_axis<1>(dir, comp, c.i0, c.i1, c.i2, v);
+  if (PML_NDIM >= 3) v = pml_dirichlet_axis<2>(dir, comp, c.i0, c.i1, c.i2, v);
 #endif
   return v;
 }
@@ -383,7 +378,7 @@ __device__ __forceinline__ void pml_first_stage_extras(int path,
   for (int j = 0; j < PML_NALG; ++j) {
     const int k = PML_ALG_IDX[j];
     a.y_next[(i64)k * PML_NCELLS + c.idx] =
-        pml_dirichlet(a, a.dir_slot_full, k, c, V[j]);
+        pml_dirichlet(a.dir_full, k, c, V[j]);
   }
 #pragma unroll
   for (int j = 0; j < PML_NLAP; ++j)
@@ -417,25 +412,25 @@ __device__ __forceinline__ void pml_stage_cell(const PmlArgs& a, bool active,
     const i64 o = (i64)k * PML_NCELLS + c.idx;
     const double y0 = first ? PML_LD(P[k] + c.idx) : PML_LD_ONCE(a.y + o);
     if (STAGE == PML_FE) {
-      PML_ST(a.y_next + o, pml_dirichlet(a, a.dir_slot, k, c, y0 + a.dt * K[j]));
+      PML_ST(a.y_next + o, pml_dirichlet(a.dir, k, c, y0 + a.dt * K[j]));
     } else if (STAGE == PML_MID1) {
-      PML_ST(a.u_out + o, pml_dirichlet(a, a.dir_slot, k, c, y0 + (a.dt / 2.0) * K[j]));
+      PML_ST(a.u_out + o, pml_dirichlet(a.dir, k, c, y0 + (a.dt / 2.0) * K[j]));
     } else if (STAGE == PML_MID2) {
-      PML_ST(a.y_next + o, pml_dirichlet(a, a.dir_slot, k, c, y0 + a.dt * K[j]));
+      PML_ST(a.y_next + o, pml_dirichlet(a.dir, k, c, y0 + a.dt * K[j]));
     } else {
       const double kk = a.dt * K[j];
       if (STAGE == PML_RK4_1) {
         PML_ST(a.acc_out + o, kk);
-        PML_ST(a.u_out + o, pml_dirichlet(a, a.dir_slot, k, c, y0 + kk / 2.0));
+        PML_ST(a.u_out + o, pml_dirichlet(a.dir, k, c, y0 + kk / 2.0));
       } else if (STAGE == PML_RK4_2) {
         PML_ST(a.acc_out + o, PML_LD_ONCE(a.acc_in + o) + 2.0 * kk);
-        PML_ST(a.u_out + o, pml_dirichlet(a, a.dir_slot, k, c, y0 + kk / 2.0));
+        PML_ST(a.u_out + o, pml_dirichlet(a.dir, k, c, y0 + kk / 2.0));
       } else if (STAGE == PML_RK4_3) {
         PML_ST(a.acc_out + o, PML_LD_ONCE(a.acc_in + o) + 2.0 * kk);
-        PML_ST(a.u_out + o, pml_dirichlet(a, a.dir_slot, k, c, y0 + kk));
+        PML_ST(a.u_out + o, pml_dirichlet(a.dir, k, c, y0 + kk));
       } else {
         PML_ST(a.y_next + o,
-               pml_dirichlet(a, a.dir_slot, k, c,
+               pml_dirichlet(a.dir, k, c,
                              y0 + pml_div6(PML_LD_ONCE(a.acc_in + o) + kk)));
       }
     }
@@ -450,7 +445,7 @@ __device__ __forceinline__ void pml_stage_cell(const PmlArgs& a, bool active,
     for (int k = 0; k < PML_C; ++k) {
       if (PML_KIND[k] == 0) continue;
       const i64 o = (i64)k * PML_NCELLS + c.idx;
-      a.u_out[o] = pml_dirichlet(a, a.dir_slot, k, c, PML_LD(a.y + o));
+      a.u_out[o] = pml_dirichlet(a.dir, k, c, PML_LD(a.y + o));
     }
   }
   if (first) pml_first_stage_extras(path, a, src, c);
@@ -551,8 +546,8 @@ PML_STAGE_KERNEL(pml_stage_rk4_4, PML_RK4_4)
 struct PmlFusedArgs {
   PmlArgs s;        // stage A: input planes, time, table slots; all outputs
   double t_eval_b;  // stage B evaluation time
-  i64 neu_slot_b;   // stage B table slots
-  i64 dir_slot_b;
+  const double* neu_b[6];  // stage B boundary tables
+  const double* dir_b[6];
 };
 
 // in-plane geometry: "x" is the contiguous mesh axis, "y" axis 1 of a 3-D mesh
@@ -722,13 +717,16 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
   const int in_lo = max(zb - 2, 0), in_hi = min(ze + 1, PML_N0 - 1);
   const int it0 = a_lo - 1, it1 = ze;  // iterations: A(i + 1) and B(i - 1)
 
-  // ---- this thread's TMA row (at most one): rows of the input tile first,
-  // then of the step-start state, then of the accumulator
+  // ---- this thread's TMA row (at most one).  Rows are numbered input tile
+  // first, then step-start state, then accumulator, and dealt out to the warps
+  // round-robin: UBLKCP takes uniform operands, so a warp issues its rows one
+  // lane at a time and every warp should have equally few of them
   constexpr int N_IN_ROWS = PML_NRING * PML_IH;
   constexpr int N_Y_ROWS = pointwise ? NK * PML_MH : 0;
   constexpr int N_ACC_ROWS = pointwise ? NK * PML_FTY : 0;
-  static_assert(N_IN_ROWS + N_Y_ROWS + N_ACC_ROWS <= PML_F_THREADS,
-                "one TMA row per thread");
+  constexpr int N_ROWS = N_IN_ROWS + N_Y_ROWS + N_ACC_ROWS;
+  constexpr int N_WARPS = PML_F_THREADS / 32;
+  static_assert(N_ROWS <= PML_F_THREADS, "one TMA row per thread");
   int job = -1;                // 0 input, 1 step-start state, 2 accumulator
   const double* job_src = nullptr;  // row start in plane 0
   unsigned job_dst = 0, job_bytes = 0;  // byte offset within a slot
@@ -741,13 +739,12 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
       return max(0, min(r0 + n, PML_FNY) - max(r0, 0));
     };
     pb_in = (unsigned)(PML_NRING * rows_in(oy - 2 * PML_FHY, PML_IH) *
-                                (wx1 - wx0) * 8);
+                       (wx1 - wx0) * 8);
     if (pointwise) {
-      pb_y = (unsigned)(NK * rows_in(oy - PML_FHY, PML_MH) *
-                                  (wx1 - wx0) * 8);
+      pb_y = (unsigned)(NK * rows_in(oy - PML_FHY, PML_MH) * (wx1 - wx0) * 8);
       pb_acc = (unsigned)(NK * rows_in(oy, PML_FTY) * (tx1 - tx0) * 8);
     }
-    int q = tid;
+    int q = (tid >> 5) + N_WARPS * (tid & 31);
     if (q < N_IN_ROWS) {
       const int rc = q / PML_IH, r = q - rc * PML_IH;  // ring component, row
       const int row = oy - 2 * PML_FHY + r;
@@ -784,17 +781,29 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
       }
     }
   }
-  const unsigned in_ring_s = pml_smem_addr(in_ring);
-  const unsigned y_ring_s = pml_smem_addr(y_ring);
-  const unsigned acc_ring_s = pml_smem_addr(acc_ring);
+  // the job's ring: byte address of slot 0 (+ row offset) and slot size
+  const unsigned job_ring =
+      (job == 0 ? pml_smem_addr(in_ring)
+                : (job == 1 ? pml_smem_addr(y_ring) : pml_smem_addr(acc_ring))) +
+      job_dst;
+  const unsigned job_slot_bytes =
+      (unsigned)(job == 0 ? IN_SLOT : (job == 1 ? YR_SLOT : ACC_SLOT)) * 8u;
 
-  // everything iteration j reads for the first time: input plane j + 2,
-  // step-start plane j + 1 (stage A), accumulator plane j - 1 (stage B)
-  auto fetch = [&](int j, int in_first) {
-    unsigned long long* bar = bars + (j - it0) % PML_FNS_P;
+  // Slot numbering: input plane p lives in slot (p - it0) mod PML_FNS_IN; the
+  // step-start plane p in slot (p - it0 - 1) mod PML_FNS_P, the accumulator
+  // plane p in slot (p - it0 + 1) mod PML_FNS_P and iteration j uses barrier
+  // (j - it0) mod PML_FNS_P -- so that in iteration j the three pointwise
+  // indices coincide (one counter).
+  //
+  // fetch(j, ...): everything iteration j reads for the first time -- input
+  // plane j + 2 (in the prologue also j and j + 1), step-start plane j + 1
+  // (stage A) and accumulator plane j - 1 (stage B); sp = pointwise slot of j,
+  // si = input slot of plane j + 2
+  auto fetch = [&](int j, int n_in, unsigned si, unsigned sp) {
+    unsigned long long* bar = bars + sp;
     if (tid == 0) {
       unsigned tx = 0;
-      for (int p = in_first; p <= j + 2; ++p)
+      for (int p = j + 3 - n_in; p <= j + 2; ++p)
         if (p >= in_lo && p <= in_hi) tx += pb_in;
       if (pointwise) {
         if (j + 1 >= a_lo && j + 1 <= a_hi) tx += pb_y;
@@ -803,25 +812,21 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
       pml_mbar_expect_tx(bar, tx);
     }
     if (job == 0) {
-      for (int p = in_first; p <= j + 2; ++p)
+      for (int k = 0; k < n_in; ++k) {
+        const int p = j + 3 - n_in + k;
         if (p >= in_lo && p <= in_hi)
-          pml_bulk_row(in_ring_s + (unsigned)((p + PML_FNS_IN) % PML_FNS_IN) *
-                                       (IN_SLOT * 8) + job_dst,
+          pml_bulk_row(job_ring + (si + 1 - n_in + k) * job_slot_bytes,
                        job_src + (i64)p * PmlAx<0>::S, job_bytes, bar);
-    } else if (job == 1) {
-      const int p = j + 1;
-      if (p >= a_lo && p <= a_hi)
-        pml_bulk_row(y_ring_s + (unsigned)((p + PML_FNS_P) % PML_FNS_P) *
-                                    (YR_SLOT * 8) + job_dst,
-                     job_src + (i64)p * PmlAx<0>::S, job_bytes, bar);
-    } else if (job == 2) {
-      const int p = j - 1;
-      if (p >= zb && p < ze)
-        pml_bulk_row(acc_ring_s + (unsigned)((p + PML_FNS_P) % PML_FNS_P) *
-                                      (ACC_SLOT * 8) + job_dst,
+      }
+    } else if (job > 0) {
+      const int p = job == 1 ? j + 1 : j - 1;
+      const bool valid = job == 1 ? (p >= a_lo && p <= a_hi) : (p >= zb && p < ze);
+      if (valid)
+        pml_bulk_row(job_ring + sp * job_slot_bytes,
                      job_src + (i64)p * PmlAx<0>::S, job_bytes, bar);
     }
   };
+  auto wrap = [](unsigned x, unsigned n) { return x >= n ? x - n : x; };
 
   if (tid == 0) {
 #pragma unroll
@@ -829,88 +834,40 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  // prologue: the first iteration needs three input planes at once
-  fetch(it0, it0);
+  // prologue: the first iteration needs three input planes at once (slots
+  // 0..2), the next PML_FDEPTH - 1 iterations one more each
+  fetch(it0, 3, 2, 0);
 #pragma unroll 1
-  for (int j = it0 + 1; j < it0 + PML_FDEPTH; ++j) fetch(j, j + 2);
+  for (int d = 1; d < PML_FDEPTH; ++d) fetch(it0 + d, 1, 2 + d, d);
 
   PmlArgs b = a;  // stage B sees its own time and table slots
   b.t_eval = f.t_eval_b;
-  b.neu_slot = f.neu_slot_b;
-  b.dir_slot = f.dir_slot_b;
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    b.neu[q] = f.neu_b[q];
+    b.dir[q] = f.dir_b[q];
+  }
 
   // loop-invariant part of the variant choice
   const int path_a_in = pml_inplane_path(in_plane, i1, i2);
   const int path_b_in = pml_inplane_path(owner, i1, i2);
 
-  // stage-A results stage B needs two iterations later
-  double ka_1[NK], y_1[NK], ka_2[NK], y_2[NK];
-#pragma unroll
-  for (int j = 0; j < NK; ++j) ka_1[j] = y_1[j] = ka_2[j] = y_2[j] = 0.0;
-
   const i64 idx0 = pml_lin(0, in_plane ? i1 : 0, in_plane ? i2 : 0);
-#pragma unroll 1
-  for (int i = it0; i <= it1; ++i) {
+  unsigned s_in = 0;   // input slot of plane i
+  unsigned s_p = 0;    // pointwise slot / barrier of iteration i
+  unsigned phase = 0;  // parity of the barrier's current use
+
+  // One iteration: stage B on plane i - 1, then stage A on plane i + 1.  ka /
+  // ys hold stage A's increment and the step-start value of this thread's cell
+  // two iterations back (plane i - 1): stage B consumes them, stage A then
+  // overwrites them for iteration i + 2.  The loop below alternates between
+  // two such register sets, so nothing is ever moved.
+  auto iteration = [&](int i, double (&ka)[NK], double (&ys)[NK]) {
     // the slots freed by the barrier that ended iteration i - 1 are refilled
-    if (i + PML_FDEPTH <= it1) fetch(i + PML_FDEPTH, i + PML_FDEPTH + 2);
-    pml_mbar_wait(bars + (i - it0) % PML_FNS_P,
-                  (unsigned)(((i - it0) / PML_FNS_P) & 1));
-    double ka_new[NK], y_new[NK];
-#pragma unroll
-    for (int j = 0; j < NK; ++j) ka_new[j] = y_new[j] = 0.0;
-    // ---- stage A on plane i + 1 (tile + halo 1), operands from the input ring
-    {
-      const int z = i + 1;
-      const bool active = in_plane && z >= a_lo && z <= a_hi;
-      const int path = (z > 0 && z < PML_N0 - 1) ? path_a_in : 0;
-      if (active) {
-        PmlCell c;
-        c.i0 = z;
-        c.i1 = i1;
-        c.i2 = i2;
-        c.idx = idx0 + (i64)z * PmlAx<0>::S;
-        PmlRingSrc<PML_IW, PML_IN_PLANE> src;
-        src.y = a.y;
-#pragma unroll
-        for (int d = -1; d <= 1; ++d)
-          src.base[d + 1] =
-              in_ring + ((z + d + PML_FNS_IN) % PML_FNS_IN) * IN_SLOT + in_cell;
-        double K[NK];
-        pml_eval_dt(path, a, src, c, a.t_eval, K);
-        double* slot = mid_ring + ((z & 3) * MID_SLOT) + mid_cell;
-        const double* yr =
-            y_ring + ((z + PML_FNS_P) % PML_FNS_P) * YR_SLOT + yr_cell;
-#pragma unroll
-        for (int j = 0; j < PML_NDT; ++j) {
-          const int k = PML_DT_IDX[j];
-          const double y0 = first ? src.template rel<0, 0, 0>(k, c)
-                                  : yr[j * PML_YR_PLANE];
-          double ua, ka = 0.0;
-          if (MODE == PML_F_MID) {
-            ua = y0 + (a.dt / 2.0) * K[j];
-          } else {
-            ka = a.dt * K[j];
-            ua = MODE == PML_F_RK4_12 ? y0 + ka / 2.0 : y0 + ka;
-          }
-          slot[pml_ring_index(k) * PML_MID_PLANE] =
-              pml_dirichlet(a, a.dir_slot, k, c, ua);
-          ka_new[j] = ka;
-          y_new[j] = y0;
-        }
-#if PML_NALG + PML_NLAP > 0
-        if (!PML_PASSTHROUGH) {
-#pragma unroll
-          for (int k = 0; k < PML_C; ++k) {
-            if (PML_KIND[k] == 0) continue;
-            slot[k * PML_MID_PLANE] = pml_dirichlet(
-                a, a.dir_slot, k, c, PML_LD(a.y + (i64)k * PML_NCELLS + c.idx));
-          }
-        }
-        if (first && owner && z >= zb && z < ze)
-          pml_first_stage_extras(path, a, src, c);
-#endif
-      }
-    }
+    if (i + PML_FDEPTH <= it1)
+      fetch(i + PML_FDEPTH, 1, wrap(s_in + PML_FDEPTH + 2, PML_FNS_IN),
+            wrap(s_p + PML_FDEPTH, PML_FNS_P));
+    pml_mbar_wait(bars + s_p, phase);
     // ---- stage B on plane i - 1 (tile cells), operands from the stage-A ring
     {
       const int z = i - 1;
@@ -929,26 +886,25 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
           src.base[d + 1] = mid_ring + (((z + d) & 3) * MID_SLOT) + mid_cell;
         double K[NK];
         pml_eval_dt(path, b, src, c, b.t_eval, K);
-        const double* ar =
-            acc_ring + ((z + PML_FNS_P) % PML_FNS_P) * ACC_SLOT + own_cell;
+        const double* ar = acc_ring + s_p * ACC_SLOT + own_cell;
 #pragma unroll
         for (int j = 0; j < PML_NDT; ++j) {
           const int k = PML_DT_IDX[j];
           const i64 o = (i64)k * PML_NCELLS + c.idx;
-          const double ka = ka_2[j], y0 = y_2[j];
+          const double y0 = ys[j];
           if (MODE == PML_F_RK4_12) {
             const double kk = b.dt * K[j];
-            PML_ST(b.acc_out + o, ka + 2.0 * kk);
+            PML_ST(b.acc_out + o, ka[j] + 2.0 * kk);
             PML_ST(b.u_out + o,
-                   pml_dirichlet(b, b.dir_slot, k, c, y0 + kk / 2.0));
+                   pml_dirichlet(b.dir, k, c, y0 + kk / 2.0));
           } else if (MODE == PML_F_RK4_34) {
             const double kk = b.dt * K[j];
-            const double acc = ar[j * PML_OWN_PLANE] + 2.0 * ka;
+            const double acc = ar[j * PML_OWN_PLANE] + 2.0 * ka[j];
             PML_ST(b.y_next + o,
-                   pml_dirichlet(b, b.dir_slot, k, c, y0 + pml_div6(acc + kk)));
+                   pml_dirichlet(b.dir, k, c, y0 + pml_div6(acc + kk)));
           } else {
             PML_ST(b.y_next + o,
-                   pml_dirichlet(b, b.dir_slot, k, c, y0 + b.dt * K[j]));
+                   pml_dirichlet(b.dir, k, c, y0 + b.dt * K[j]));
           }
         }
 #if PML_NALG + PML_NLAP > 0
@@ -957,20 +913,79 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
           for (int k = 0; k < PML_C; ++k) {
             if (PML_KIND[k] == 0) continue;
             const i64 o = (i64)k * PML_NCELLS + c.idx;
-            b.u_out[o] = pml_dirichlet(b, b.dir_slot, k, c, PML_LD(b.y + o));
+            b.u_out[o] = pml_dirichlet(b.dir, k, c, PML_LD(b.y + o));
           }
         }
 #endif
       }
     }
+    // ---- stage A on plane i + 1 (tile + halo 1), operands from the input ring
+    {
+      const int z = i + 1;
+      const bool active = in_plane && z >= a_lo && z <= a_hi;
+      const int path = (z > 0 && z < PML_N0 - 1) ? path_a_in : 0;
+      if (active) {
+        PmlCell c;
+        c.i0 = z;
+        c.i1 = i1;
+        c.i2 = i2;
+        c.idx = idx0 + (i64)z * PmlAx<0>::S;
+        PmlRingSrc<PML_IW, PML_IN_PLANE> src;
+        src.y = a.y;
 #pragma unroll
-    for (int j = 0; j < NK; ++j) {
-      ka_2[j] = ka_1[j];
-      y_2[j] = y_1[j];
-      ka_1[j] = ka_new[j];
-      y_1[j] = y_new[j];
+        for (int d = 0; d < 3; ++d)
+          src.base[d] =
+              in_ring + wrap(s_in + d, PML_FNS_IN) * IN_SLOT + in_cell;
+        double K[NK];
+        pml_eval_dt(path, a, src, c, a.t_eval, K);
+        double* slot = mid_ring + ((z & 3) * MID_SLOT) + mid_cell;
+        const double* yr = y_ring + s_p * YR_SLOT + yr_cell;
+#pragma unroll
+        for (int j = 0; j < PML_NDT; ++j) {
+          const int k = PML_DT_IDX[j];
+          const double y0 = first ? src.template rel<0, 0, 0>(k, c)
+                                  : yr[j * PML_YR_PLANE];
+          double ua, kk = 0.0;
+          if (MODE == PML_F_MID) {
+            ua = y0 + (a.dt / 2.0) * K[j];
+          } else {
+            kk = a.dt * K[j];
+            ua = MODE == PML_F_RK4_12 ? y0 + kk / 2.0 : y0 + kk;
+          }
+          slot[pml_ring_index(k) * PML_MID_PLANE] =
+              pml_dirichlet(a.dir, k, c, ua);
+          ka[j] = kk;
+          ys[j] = y0;
+        }
+#if PML_NALG + PML_NLAP > 0
+        if (!PML_PASSTHROUGH) {
+#pragma unroll
+          for (int k = 0; k < PML_C; ++k) {
+            if (PML_KIND[k] == 0) continue;
+            slot[k * PML_MID_PLANE] = pml_dirichlet(
+                a.dir, k, c, PML_LD(a.y + (i64)k * PML_NCELLS + c.idx));
+          }
+        }
+        if (first && owner && z >= zb && z < ze)
+          pml_first_stage_extras(path, a, src, c);
+#endif
+      }
+    }
+    s_in = wrap(s_in + 1, PML_FNS_IN);
+    if (++s_p == PML_FNS_P) {
+      s_p = 0;
+      phase ^= 1u;
     }
     __syncthreads();
+  };
+
+  double ka_e[NK], ys_e[NK], ka_o[NK], ys_o[NK];
+#pragma unroll
+  for (int j = 0; j < NK; ++j) ka_e[j] = ys_e[j] = ka_o[j] = ys_o[j] = 0.0;
+#pragma unroll 1
+  for (int i = it0; i <= it1; i += 2) {
+    iteration(i, ka_e, ys_e);
+    if (i + 1 <= it1) iteration(i + 1, ka_o, ys_o);
   }
 }
 
@@ -995,7 +1010,10 @@ PML_FUSED_KERNEL(pml_fused_mid, PML_F_MID)
 // ---------------------------------------------------------------------------
 #if PML_SMALL
 struct PmlSmallArgs {
-  PmlArgs s;        // tables, d_t; s.y = state before the first step
+  PmlArgs s;        // d_t, coordinates; s.y = state before the first step;
+                    // s.neu / s.dir = slot 0 of the boundary tables
+  i64 neu_stride[6];  // doubles per time slot (0 = static)
+  i64 dir_stride[6];
   double* traj;     // trajectory slots
   i64 stride;
   const double* t;  // start time of every step (device)
@@ -1021,14 +1039,19 @@ __device__ __forceinline__ void pml_small_stage(const PmlArgs& a) {
   __syncthreads();
 }
 
-__device__ __forceinline__ void pml_small_set(PmlArgs& a, const double* u,
-                                              double* u_out, double t_eval,
-                                              i64 neu_slot, i64 dir_slot) {
+__device__ __forceinline__ void pml_small_set(PmlArgs& a,
+                                              const PmlSmallArgs& f,
+                                              const double* u, double* u_out,
+                                              double t_eval, i64 neu_slot,
+                                              i64 dir_slot) {
   a.u = u;
   a.u_out = u_out;
   a.t_eval = t_eval;
-  a.neu_slot = neu_slot;
-  a.dir_slot = dir_slot;
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    a.neu[q] = f.s.neu[q] + neu_slot * f.neu_stride[q];
+    a.dir[q] = f.s.dir[q] + dir_slot * f.dir_stride[q];
+  }
 }
 
 extern "C" __global__ void __launch_bounds__(PML_SMALL_THREADS)
@@ -1043,23 +1066,25 @@ extern "C" __global__ void __launch_bounds__(PML_SMALL_THREADS)
     a.y = y;
     a.y_next = f.traj + (i64)j * f.stride;
     const i64 s_t = f.slot0 + 3 * (i64)j, s_h = s_t + 1, s_f = s_t + 2;
-    a.dir_slot_full = s_f;
+#pragma unroll
+    for (int q = 0; q < 6; ++q)
+      a.dir_full[q] = f.s.dir[q] + s_f * f.dir_stride[q];
     if (f.integrator == 0) {
-      pml_small_set(a, y, nullptr, t, s_t, s_f);
+      pml_small_set(a, f, y, nullptr, t, s_t, s_f);
       pml_small_stage<PML_FE>(a);
     } else if (f.integrator == 1) {
-      pml_small_set(a, y, f.u_a, t, s_t, s_h);
+      pml_small_set(a, f, y, f.u_a, t, s_t, s_h);
       pml_small_stage<PML_MID1>(a);
-      pml_small_set(a, f.u_a, nullptr, t + half, s_h, s_f);
+      pml_small_set(a, f, f.u_a, nullptr, t + half, s_h, s_f);
       pml_small_stage<PML_MID2>(a);
     } else {
-      pml_small_set(a, y, f.u_a, t, s_t, s_h);
+      pml_small_set(a, f, y, f.u_a, t, s_t, s_h);
       pml_small_stage<PML_RK4_1>(a);
-      pml_small_set(a, f.u_a, f.u_b, t + half, s_h, s_h);
+      pml_small_set(a, f, f.u_a, f.u_b, t + half, s_h, s_h);
       pml_small_stage<PML_RK4_2>(a);
-      pml_small_set(a, f.u_b, f.u_a, t + half, s_h, s_f);
+      pml_small_set(a, f, f.u_b, f.u_a, t + half, s_h, s_f);
       pml_small_stage<PML_RK4_3>(a);
-      pml_small_set(a, f.u_a, nullptr, t + dt, s_f, s_f);
+      pml_small_set(a, f, f.u_a, nullptr, t + dt, s_f, s_f);
       pml_small_stage<PML_RK4_4>(a);
     }
   }
@@ -1088,7 +1113,7 @@ extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ)
 // ---------------------------------------------------------------------------
 #if PML_NLAP > 0
 struct PmlJacobiArgs {
-  PmlArgs base;            // tables; neu_slot / dir_slot are those of t + dt
+  PmlArgs base;            // tables: neu / dir are those of t + dt
   const double* y_hat;     // NLAP planes
   const double* rhs;       // NLAP planes
   double* y_new;           // NLAP planes
@@ -1105,7 +1130,7 @@ extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ)
 #pragma unroll
   for (int j = 0; j < PML_NLAP; ++j)
     out[(i64)j * PML_NCELLS + c.idx] = pml_dirichlet(
-        a, a.dir_slot, PML_LAP_IDX[j], c, y_init[c.idx * PML_NLAP + j]);
+        a.dir, PML_LAP_IDX[j], c, y_init[c.idx * PML_NLAP + j]);
 }
 
 extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ)
@@ -1165,7 +1190,7 @@ extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ)
       acc -= PML_LD(j.rhs + (i64)q * PML_NCELLS + c.idx);
       const double v = acc / diag;
 #endif
-      const double vn = pml_dirichlet(a, a.dir_slot, comp, c, v);
+      const double vn = pml_dirichlet(a.dir, comp, c, v);
       j.y_new[(i64)q * PML_NCELLS + c.idx] = vn;
       const double d = vn - PML_LD(p + c.idx);
       sq += d * d;

@@ -101,13 +101,9 @@ struct PmlArgs {
   double* lap_rhs;
   double t_eval;
   double dt;
-  long long neu_slot;
-  long long dir_slot;
-  long long dir_slot_full;
   const double* neu[6];
-  long long neu_stride[6];
   const double* dir[6];
-  long long dir_stride[6];
+  const double* dir_full[6];
   const double* coord[3];
   const double* aux[4];
 };
@@ -115,12 +111,14 @@ struct PmlArgs {
 struct PmlFusedArgs {
   PmlArgs s;
   double t_eval_b;
-  long long neu_slot_b;
-  long long dir_slot_b;
+  const double* neu_b[6];
+  const double* dir_b[6];
 };
 
 struct PmlSmallArgs {
   PmlArgs s;
+  long long neu_stride[6];
+  long long dir_stride[6];
   double* traj;
   long long stride;
   const double* t;
@@ -211,13 +209,21 @@ struct pml_plan {
 
 namespace {
 
+// boundary tables at their time slots: the kernels receive ready pointers
+void bind_neu(const pml_plan* p, const double** neu, long long slot) {
+  for (int f = 0; f < 6; ++f)
+    neu[f] = p->tables.neu[f]
+                 ? p->tables.neu[f] + slot * p->tables.neu_stride[f] : nullptr;
+}
+void bind_dir(const pml_plan* p, const double** dir, long long slot) {
+  for (int f = 0; f < 6; ++f)
+    dir[f] = p->tables.dir[f]
+                 ? p->tables.dir[f] + slot * p->tables.dir_stride[f] : nullptr;
+}
 void fill_tables(const pml_plan* p, PmlArgs& a) {
-  for (int f = 0; f < 6; ++f) {
-    a.neu[f] = p->tables.neu[f];
-    a.neu_stride[f] = p->tables.neu_stride[f];
-    a.dir[f] = p->tables.dir[f];
-    a.dir_stride[f] = p->tables.dir_stride[f];
-  }
+  bind_neu(p, a.neu, 0);
+  bind_dir(p, a.dir, 0);
+  bind_dir(p, a.dir_full, 0);
   for (int i = 0; i < 3; ++i) a.coord[i] = p->tables.coord[i];
   for (int i = 0; i < 4; ++i) a.aux[i] = p->tables.aux[i];
 }
@@ -466,6 +472,10 @@ int pml_fdm_run(pml_plan* p, int integrator, const pml_workspace* ws,
                                cudaMemcpyHostToDevice, (cudaStream_t)s));
       PmlSmallArgs f;
       f.s = a;
+      for (int q = 0; q < 6; ++q) {
+        f.neu_stride[q] = p->tables.neu_stride[q];
+        f.dir_stride[q] = p->tables.dir_stride[q];
+      }
       f.s.y = first == 0 ? y0 : traj + (long long)(first - 1) * stride;
       f.traj = traj + (long long)first * stride;
       f.stride = stride;
@@ -493,7 +503,7 @@ int pml_fdm_run(pml_plan* p, int integrator, const pml_workspace* ws,
     const long long s_t = slot0 + 3LL * j, s_h = s_t + 1, s_f = s_t + 2;
     a.y = y;
     a.y_next = y_next;
-    a.dir_slot_full = s_f;
+    bind_dir(p, a.dir_full, s_f);
     void* params[] = {&a};
     auto stage = [&](int k, const double* u, double* u_out, double t_eval,
                      long long neu_slot, long long dir_slot) {
@@ -502,8 +512,8 @@ int pml_fdm_run(pml_plan* p, int integrator, const pml_workspace* ws,
       a.acc_in = ws->acc;
       a.acc_out = ws->acc;
       a.t_eval = t_eval;
-      a.neu_slot = neu_slot;
-      a.dir_slot = dir_slot;
+      bind_neu(p, a.neu, neu_slot);
+      bind_dir(p, a.dir, dir_slot);
       CUresult r_ = g_drv.launchKernel(p->stage[k], p->sgrid.x, p->sgrid.y,
                                        p->sgrid.z, p->block.x, p->block.y,
                                        p->block.z, 0, s, params, nullptr);
@@ -520,12 +530,12 @@ int pml_fdm_run(pml_plan* p, int integrator, const pml_workspace* ws,
       a.acc_in = ws->acc;
       a.acc_out = ws->acc;
       a.t_eval = t_a;
-      a.neu_slot = neu_a;
-      a.dir_slot = dir_a;
+      bind_neu(p, a.neu, neu_a);
+      bind_dir(p, a.dir, dir_a);
       f.s = a;
       f.t_eval_b = t_b;
-      f.neu_slot_b = neu_b;
-      f.dir_slot_b = dir_b;
+      bind_neu(p, f.neu_b, neu_b);
+      bind_dir(p, f.dir_b, dir_b);
       void* fparams[] = {&f};
       CUresult r_ = g_drv.launchKernel(p->fused[k], p->fgrid.x, p->fgrid.y,
                                        p->fgrid.z, p->fblock.x, p->fblock.y, 1,
@@ -559,8 +569,8 @@ int pml_fdm_run(pml_plan* p, int integrator, const pml_workspace* ws,
     if (rc) return rc;
     if (p->desc.n_lap > 0) {
       PmlArgs tbl = a;
-      tbl.neu_slot = s_f;
-      tbl.dir_slot = s_f;
+      bind_neu(p, tbl.neu, s_f);
+      bind_dir(p, tbl.dir, s_f);
       int sweeps = 0;
       if (jacobi_solve(p, ws, tbl, ws->lap_rhs, jacobi_init + (long long)j * lap_elems,
                        y_next, jacobi_tol, max_sweeps, &sweeps, s))
@@ -581,9 +591,9 @@ int pml_eval_rhs(pml_plan* p, const double* u, double* out, double t,
   a.y = u;
   a.u_out = out;
   a.t_eval = t;
-  a.neu_slot = slot;
-  a.dir_slot = slot;
-  a.dir_slot_full = slot;
+  bind_neu(p, a.neu, slot);
+  bind_dir(p, a.dir, slot);
+  bind_dir(p, a.dir_full, slot);
   void* params[] = {&a};
   return launch(p, p->eval_rhs, params, (CUstream)stream);
 }
@@ -597,9 +607,9 @@ int pml_jacobi_run(pml_plan* p, const pml_workspace* ws, const double* rhs,
   PmlArgs a;
   std::memset(&a, 0, sizeof(a));
   fill_tables(p, a);
-  a.neu_slot = slot;
-  a.dir_slot = slot;
-  a.dir_slot_full = slot;
+  bind_neu(p, a.neu, slot);
+  bind_dir(p, a.dir, slot);
+  bind_dir(p, a.dir_full, slot);
   return jacobi_solve(p, ws, a, rhs, y_init, y_next, tol, max_sweeps,
                       sweeps_out, (CUstream)stream);
 }

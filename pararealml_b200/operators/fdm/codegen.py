@@ -161,7 +161,9 @@ def default_fused(shape, y_dim, n_dt=None, passthrough=False) -> Optional[FusedT
     if os.environ.get("PML_FTILE"):
         tx, ty = (int(v) for v in os.environ["PML_FTILE"].split(","))
     elif nd == 3:
-        tx, ty = 32, 16
+        # tile + halo 1 = 32 cells per row: one warp per row of the stage-A
+        # tile (conflict-free shared-memory rows, warp-uniform row predicates)
+        tx, ty = 30, 16
     else:
         tx, ty = 254, 1
     if nd == 2:

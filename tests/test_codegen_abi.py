@@ -35,7 +35,7 @@ def test_library_exports_every_symbol_of_the_header():
 
 
 def test_struct_layouts_match_the_header():
-    assert ctypes.sizeof(_native.PlanDesc) == 4 * 17
+    assert ctypes.sizeof(_native.PlanDesc) == 4 * 20
     assert ctypes.sizeof(_native.Tables) == 8 * (6 * 4 + 3 + 4)
     assert ctypes.sizeof(_native.Workspace) == 8 * 10
 
