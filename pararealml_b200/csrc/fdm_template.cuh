@@ -544,6 +544,12 @@ PML_STAGE_KERNEL(pml_stage_rk4_4, PML_RK4_4)
 // ---------------------------------------------------------------------------
 #if PML_FUSED
 struct PmlFusedArgs {
+  // TMA descriptors (CUtensorMap, encoded by the host per launch) of the 4-D
+  // arrays [component][axis 0][axis 1][contiguous axis]: stage A's stencil
+  // input, the step-start state and the accumulator (the latter two: 3+4 only)
+  alignas(64) unsigned char tm_in[128];
+  alignas(64) unsigned char tm_y[128];
+  alignas(64) unsigned char tm_acc[128];
   PmlArgs s;        // stage A: input planes, time, table slots; all outputs
   double t_eval_b;  // stage B evaluation time
   const double* neu_b[6];  // stage B boundary tables
@@ -565,9 +571,11 @@ struct PmlFusedArgs {
 #define PML_IW (PML_FTX + 4)              // input tile (halo 2)
 #define PML_IH (PML_FTY + 4 * PML_FHY)
 #define PML_MID_PLANE (PML_MW * PML_MH)
-#define PML_IN_PLANE (PML_IW * PML_IH)
-#define PML_YR_PLANE (PML_IW * PML_MH)    // step-start state: rows of stage A
-#define PML_OWN_PLANE (PML_FTX * PML_FTY)
+// TMA boxes land on 128-byte boundaries: component planes are padded to 16 doubles
+#define PML_PAD16(n) (((n) + 15) / 16 * 16)
+#define PML_IN_PLANE PML_PAD16(PML_IW * PML_IH)
+#define PML_YR_PLANE PML_PAD16(PML_IW * PML_MH)  // step-start state: rows of stage A
+#define PML_OWN_PLANE PML_PAD16(PML_FTX * PML_FTY)
 // components held in the rings: all of them, or only the time-stepped ones when
 // the others are read from the step-start state directly (PML_PASSTHROUGH)
 #define PML_NRING (PML_PASSTHROUGH ? (PML_NDT > 0 ? PML_NDT : 1) : PML_C)
@@ -636,15 +644,17 @@ __device__ __forceinline__ void pml_mbar_wait(unsigned long long* bar,
         : "memory");
   } while (!ok);
 }
-// one row global -> shared through the TMA unit; completion is signalled on
-// the mbarrier (16-byte aligned addresses, size a multiple of 16 bytes)
-__device__ __forceinline__ void pml_bulk_row(unsigned dst, const double* src,
-                                             unsigned bytes,
-                                             unsigned long long* bar) {
+// one box (rows x columns of one component plane) global -> shared through the
+// TMA unit; cells outside the array arrive as zeros; completion (box bytes) is
+// signalled on the mbarrier
+__device__ __forceinline__ void pml_tma_box(unsigned dst, const void* tmap,
+                                            int x, int y, int z, int comp,
+                                            unsigned long long* bar) {
   asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
-      "[%0], [%1], %2, [%3];" ::"r"(dst),
-      "l"(src), "r"(bytes), "r"(pml_smem_addr(bar))
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::"
+      "complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+      "l"((unsigned long long)tmap), "r"(x), "r"(y), "r"(z), "r"(comp),
+      "r"(pml_smem_addr(bar))
       : "memory");
 }
 
@@ -679,7 +689,7 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
   constexpr int ACC_SLOT = NK * PML_OWN_PLANE;
   double* in_ring = smem;
   double* mid_ring = in_ring + PML_FNS_IN * IN_SLOT;
-  double* y_ring = mid_ring + 4 * MID_SLOT;
+  double* y_ring = mid_ring + PML_PAD16(4 * MID_SLOT);  // 128-byte aligned
   double* acc_ring = y_ring + PML_FNS_P * YR_SLOT;
   const int tid = threadIdx.x;
 
@@ -717,77 +727,54 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
   const int in_lo = max(zb - 2, 0), in_hi = min(ze + 1, PML_N0 - 1);
   const int it0 = a_lo - 1, it1 = ze;  // iterations: A(i + 1) and B(i - 1)
 
-  // ---- this thread's TMA row (at most one).  Rows are numbered input tile
-  // first, then step-start state, then accumulator, and dealt out to the warps
-  // round-robin: UBLKCP takes uniform operands, so a warp issues its rows one
-  // lane at a time and every warp should have equally few of them
-  constexpr int N_IN_ROWS = PML_NRING * PML_IH;
-  constexpr int N_Y_ROWS = pointwise ? NK * PML_MH : 0;
-  constexpr int N_ACC_ROWS = pointwise ? NK * PML_FTY : 0;
-  constexpr int N_ROWS = N_IN_ROWS + N_Y_ROWS + N_ACC_ROWS;
+  // ---- this thread's TMA box (at most one): one component plane of the
+  // input tile, of the step-start state or of the accumulator.  Boxes are dealt
+  // out to the warps round-robin (the copy instruction takes uniform operands,
+  // so a warp issues its boxes one lane at a time)
+  constexpr int N_IN_BOX = PML_NRING;
+  constexpr int N_Y_BOX = pointwise ? NK : 0;
+  constexpr int N_BOX = N_IN_BOX + 2 * N_Y_BOX;
   constexpr int N_WARPS = PML_F_THREADS / 32;
-  static_assert(N_ROWS <= PML_F_THREADS, "one TMA row per thread");
-  int job = -1;                // 0 input, 1 step-start state, 2 accumulator
-  const double* job_src = nullptr;  // row start in plane 0
-  unsigned job_dst = 0, job_bytes = 0;  // byte offset within a slot
-  unsigned pb_in = 0, pb_y = 0, pb_acc = 0;  // bytes per plane of each ring
+  static_assert(N_BOX <= PML_F_THREADS, "one TMA box per thread");
+  constexpr unsigned IN_BOX_BYTES = PML_IW * PML_IH * 8;
+  constexpr unsigned Y_BOX_BYTES = PML_IW * PML_MH * 8;
+  constexpr unsigned ACC_BOX_BYTES = PML_FTX * PML_FTY * 8;
+  int job = -1;  // 0 input, 1 step-start state, 2 accumulator
+  int job_comp = 0, job_x = 0, job_y = 0;
+  unsigned job_ring = 0, job_slot_bytes = 0;
+  const void* job_map = nullptr;
   {
-    // x range of the wide rows (input, step-start state) and the tile rows
-    const int wx0 = max(ox - 2, 0), wx1 = min(ox + PML_FTX + 2, PML_FNX);
-    const int tx0 = ox, tx1 = min(ox + PML_FTX, PML_FNX);
-    auto rows_in = [&](int r0, int n) {  // rows of [r0, r0 + n) inside the mesh
-      return max(0, min(r0 + n, PML_FNY) - max(r0, 0));
-    };
-    pb_in = (unsigned)(PML_NRING * rows_in(oy - 2 * PML_FHY, PML_IH) *
-                       (wx1 - wx0) * 8);
-    if (pointwise) {
-      pb_y = (unsigned)(NK * rows_in(oy - PML_FHY, PML_MH) * (wx1 - wx0) * 8);
-      pb_acc = (unsigned)(NK * rows_in(oy, PML_FTY) * (tx1 - tx0) * 8);
-    }
     int q = (tid >> 5) + N_WARPS * (tid & 31);
-    if (q < N_IN_ROWS) {
-      const int rc = q / PML_IH, r = q - rc * PML_IH;  // ring component, row
-      const int row = oy - 2 * PML_FHY + r;
-      int comp = 0;  // component held at ring index rc
+    if (q < N_IN_BOX) {
+      job = 0;
+      // component held at ring index q
 #pragma unroll
       for (int k = 0; k < PML_C; ++k)
-        if ((!PML_PASSTHROUGH || PML_KIND[k] == 0) && pml_ring_index(k) == rc)
-          comp = k;
-      if (row >= 0 && row < PML_FNY) {
-        job = 0;
-        const double* base =
-            (first || (PML_PASSTHROUGH && PML_KIND[comp] != 0)) ? a.y : a.u;
-        job_src = base + (i64)comp * PML_NCELLS + (i64)row * PML_FNX + wx0;
-        job_dst = (unsigned)(((rc * PML_IH + r) * PML_IW + (wx0 - (ox - 2))) * 8);
-        job_bytes = (unsigned)((wx1 - wx0) * 8);
-      }
-    } else if (pointwise && (q -= N_IN_ROWS) < N_Y_ROWS) {
-      const int j = q / PML_MH, r = q - j * PML_MH;
-      const int row = oy - PML_FHY + r;
-      if (row >= 0 && row < PML_FNY) {
-        job = 1;
-        job_src = a.y + (i64)PML_DT_IDX[j] * PML_NCELLS + (i64)row * PML_FNX + wx0;
-        job_dst = (unsigned)(((j * PML_MH + r) * PML_IW + (wx0 - (ox - 2))) * 8);
-        job_bytes = (unsigned)((wx1 - wx0) * 8);
-      }
-    } else if (pointwise && (q -= N_Y_ROWS) < N_ACC_ROWS) {
-      const int j = q / PML_FTY, r = q - j * PML_FTY;
-      const int row = oy + r;
-      if (row < PML_FNY) {
-        job = 2;
-        job_src = a.acc_in + (i64)PML_DT_IDX[j] * PML_NCELLS + (i64)row * PML_FNX + tx0;
-        job_dst = (unsigned)(((j * PML_FTY + r) * PML_FTX) * 8);
-        job_bytes = (unsigned)((tx1 - tx0) * 8);
-      }
+        if ((!PML_PASSTHROUGH || PML_KIND[k] == 0) && pml_ring_index(k) == q)
+          job_comp = k;
+      job_x = ox - 2;
+      job_y = oy - 2 * PML_FHY;
+      job_ring = pml_smem_addr(in_ring) + (unsigned)q * (PML_IN_PLANE * 8);
+      job_slot_bytes = IN_SLOT * 8;
+      job_map = f.tm_in;
+    } else if (pointwise && (q -= N_IN_BOX) < N_Y_BOX) {
+      job = 1;
+      job_comp = PML_DT_IDX[q];
+      job_x = ox - 2;
+      job_y = oy - PML_FHY;
+      job_ring = pml_smem_addr(y_ring) + (unsigned)q * (PML_YR_PLANE * 8);
+      job_slot_bytes = YR_SLOT * 8;
+      job_map = f.tm_y;
+    } else if (pointwise && (q -= N_Y_BOX) < N_Y_BOX) {
+      job = 2;
+      job_comp = PML_DT_IDX[q];
+      job_x = ox;
+      job_y = oy;
+      job_ring = pml_smem_addr(acc_ring) + (unsigned)q * (PML_OWN_PLANE * 8);
+      job_slot_bytes = ACC_SLOT * 8;
+      job_map = f.tm_acc;
     }
   }
-  // the job's ring: byte address of slot 0 (+ row offset) and slot size
-  const unsigned job_ring =
-      (job == 0 ? pml_smem_addr(in_ring)
-                : (job == 1 ? pml_smem_addr(y_ring) : pml_smem_addr(acc_ring))) +
-      job_dst;
-  const unsigned job_slot_bytes =
-      (unsigned)(job == 0 ? IN_SLOT : (job == 1 ? YR_SLOT : ACC_SLOT)) * 8u;
 
   // Slot numbering: input plane p lives in slot (p - it0) mod PML_FNS_IN; the
   // step-start plane p in slot (p - it0 - 1) mod PML_FNS_P, the accumulator
@@ -804,10 +791,10 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
     if (tid == 0) {
       unsigned tx = 0;
       for (int p = j + 3 - n_in; p <= j + 2; ++p)
-        if (p >= in_lo && p <= in_hi) tx += pb_in;
+        if (p >= in_lo && p <= in_hi) tx += N_IN_BOX * IN_BOX_BYTES;
       if (pointwise) {
-        if (j + 1 >= a_lo && j + 1 <= a_hi) tx += pb_y;
-        if (j - 1 >= zb && j - 1 < ze) tx += pb_acc;
+        if (j + 1 >= a_lo && j + 1 <= a_hi) tx += N_Y_BOX * Y_BOX_BYTES;
+        if (j - 1 >= zb && j - 1 < ze) tx += N_Y_BOX * ACC_BOX_BYTES;
       }
       pml_mbar_expect_tx(bar, tx);
     }
@@ -815,15 +802,15 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
       for (int k = 0; k < n_in; ++k) {
         const int p = j + 3 - n_in + k;
         if (p >= in_lo && p <= in_hi)
-          pml_bulk_row(job_ring + (si + 1 - n_in + k) * job_slot_bytes,
-                       job_src + (i64)p * PmlAx<0>::S, job_bytes, bar);
+          pml_tma_box(job_ring + (si + 1 - n_in + k) * job_slot_bytes, job_map,
+                      job_x, job_y, p, job_comp, bar);
       }
     } else if (job > 0) {
       const int p = job == 1 ? j + 1 : j - 1;
       const bool valid = job == 1 ? (p >= a_lo && p <= a_hi) : (p >= zb && p < ze);
       if (valid)
-        pml_bulk_row(job_ring + sp * job_slot_bytes,
-                     job_src + (i64)p * PmlAx<0>::S, job_bytes, bar);
+        pml_tma_box(job_ring + sp * job_slot_bytes, job_map, job_x, job_y, p,
+                    job_comp, bar);
     }
   };
   auto wrap = [](unsigned x, unsigned n) { return x >= n ? x - n : x; };

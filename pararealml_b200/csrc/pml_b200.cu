@@ -50,6 +50,11 @@ struct Driver {
                            void**) = nullptr;
   CUresult (*getErrorString)(CUresult, const char**) = nullptr;
   CUresult (*funcSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
+  CUresult (*tensorMapEncodeTiled)(
+      CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+      CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+      CUtensorMapFloatOOBfill) = nullptr;
   bool ready = false;
 };
 Driver g_drv;
@@ -67,6 +72,7 @@ int load_driver() {
       {"cuLaunchKernel", (void**)&g_drv.launchKernel},
       {"cuGetErrorString", (void**)&g_drv.getErrorString},
       {"cuFuncSetAttribute", (void**)&g_drv.funcSetAttribute},
+      {"cuTensorMapEncodeTiled", (void**)&g_drv.tensorMapEncodeTiled},
   };
   for (auto& s : syms) {
     cudaDriverEntryPointQueryResult q;
@@ -109,6 +115,9 @@ struct PmlArgs {
 };
 
 struct PmlFusedArgs {
+  alignas(64) CUtensorMap tm_in;
+  alignas(64) CUtensorMap tm_y;
+  alignas(64) CUtensorMap tm_acc;
   PmlArgs s;
   double t_eval_b;
   const double* neu_b[6];
@@ -220,6 +229,27 @@ void bind_dir(const pml_plan* p, const double** dir, long long slot) {
     dir[f] = p->tables.dir[f]
                  ? p->tables.dir[f] + slot * p->tables.dir_stride[f] : nullptr;
 }
+// TMA descriptor of a state (component planes) seen as the 4-D array
+// [component][axis 0][axis 1][contiguous axis] with a box of one plane tile
+int state_tensor_map(const pml_plan* p, const double* base, unsigned box_x,
+                     unsigned box_y, CUtensorMap* out) {
+  const pml_plan_desc& d = p->desc;
+  const bool three = d.n_dims == 3;
+  const cuuint64_t nx = (cuuint64_t)(three ? d.shape[2] : d.shape[1]);
+  const cuuint64_t ny = (cuuint64_t)(three ? d.shape[1] : 1);
+  const cuuint64_t nz = (cuuint64_t)d.shape[0];
+  const cuuint64_t dims[4] = {nx, ny, nz, (cuuint64_t)d.y_dim};
+  const cuuint64_t strides[3] = {nx * 8, nx * ny * 8, nx * ny * nz * 8};
+  const cuuint32_t box[4] = {box_x, box_y, 1, 1};
+  const cuuint32_t elem[4] = {1, 1, 1, 1};
+  CUresult r = g_drv.tensorMapEncodeTiled(
+      out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void*)base, dims, strides, box,
+      elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled: " + cu_err(r));
+  return 0;
+}
+
 void fill_tables(const pml_plan* p, PmlArgs& a) {
   bind_neu(p, a.neu, 0);
   bind_dir(p, a.dir, 0);
@@ -525,6 +555,17 @@ int pml_fdm_run(pml_plan* p, int integrator, const pml_workspace* ws,
                      long long neu_a, long long dir_a, double t_b,
                      long long neu_b, long long dir_b) {
       PmlFusedArgs f;
+      std::memset(&f, 0, sizeof(f));
+      const unsigned ftx = (unsigned)p->desc.fused_tile[0];
+      const unsigned fty = (unsigned)p->desc.fused_tile[1];
+      const unsigned hy = p->desc.n_dims == 3 ? 1u : 0u;
+      // stage A's stencil input (tile + halo 2); for stages 3+4 also the
+      // step-start state (rows of the stage-A tile) and the accumulator
+      if (state_tensor_map(p, u, ftx + 4, fty + 4 * hy, &f.tm_in)) return -1;
+      if (k == 1) {
+        if (state_tensor_map(p, y, ftx + 4, fty + 2 * hy, &f.tm_y)) return -1;
+        if (state_tensor_map(p, ws->acc, ftx, fty, &f.tm_acc)) return -1;
+      }
       a.u = u;
       a.u_out = u_out;
       a.acc_in = ws->acc;

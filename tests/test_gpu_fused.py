@@ -118,7 +118,7 @@ PROBLEMS = {
     "convection_diffusion_3d_mixed": (
         convection_diffusion_3d_mixed, (23, 19, 38), "16,8", "8"),
     "cahn_hilliard_3d": (cahn_hilliard_3d, (18, 21, 34), "16,8", "8"),
-    "diffusion_2d_multi_tile": (diffusion_2d, (150, 600), "254,1", "32"),
+    "diffusion_2d_multi_tile": (diffusion_2d, (150, 600), "222,1", "32"),
     "diffusion_2d_small_tiles": (diffusion_2d, (45, 50), "16,1", "11"),
     "shallow_water_polar": (shallow_water_polar, (70, 300), "126,1", "24"),
 }
