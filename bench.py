@@ -584,7 +584,7 @@ def run_b200(args):
                 "traffic": traffic,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_cell_step": 128 * y_dim,
-                "launches_per_step": 4,
+                "launches_per_step": launches // max(args.steps, 1),
             },
             "cpu_baseline": cpu,
             "e2e": e2e,

@@ -151,12 +151,18 @@ def default_fused(shape, y_dim, n_dt=None, passthrough=False) -> Optional[FusedT
     """Tile of the fused stage-pair kernels: the stage-A tile (tile + halo 1)
     has one thread per cell, rows are moved by the TMA unit and therefore have
     to start on 16-byte boundaries (even extent of the contiguous axis)."""
-    mode = os.environ.get("PML_FUSE", "0")
-    if mode != "1":
+    mode = os.environ.get("PML_FUSE", "auto")
+    if mode == "0":
         return None
     nd = len(shape)
     n_dt = y_dim if n_dt is None else n_dt
     if nd < 2 or any(n < 3 for n in shape) or n_dt < 1 or shape[-1] % 2:
+        return None
+    # by default only systems whose components are all time-stepped: algebraic
+    # (LHS.Y) and Poisson components are stencil inputs that never change
+    # within a step, which the unfused kernels serve from L2 at no extra cost
+    # (measured: Cahn-Hilliard 256^3 runs 1.8x faster unfused)
+    if mode != "1" and n_dt != y_dim:
         return None
     if os.environ.get("PML_FTILE"):
         tx, ty = (int(v) for v in os.environ["PML_FTILE"].split(","))
