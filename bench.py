@@ -55,6 +55,9 @@ def parse_args():
     p.add_argument("--cpu-grid", type=int, default=96)
     p.add_argument("--cpu-parareal-grid", type=int, default=48,
                    help="vertices per axis of the host-process Parareal sample")
+    p.add_argument("--jacobi-sweeps", type=int, default=100,
+                   help="cap on Jacobi sweeps per step (navier_stokes_2d; the "
+                        "reference iterates to tolerance, 1e3..1e7 sweeps)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     return p.parse_args()
@@ -179,6 +182,28 @@ def diffusion_2d_problem(ns, n, n_steps, d_t=None):
     return ns.InitialValueProblem(cp, (0.0, n_steps * d_t), ic), d_t
 
 
+def navier_stokes_problem(ns, n, n_steps, d_t=None):
+    """K4b: NavierStokesEquation(5000) (vorticity / stream function / velocity,
+    LHS = [D_Y_OVER_D_T, Y_LAPLACIAN, Y, Y]) with the boundary conditions of
+    examples/navier_stokes_fdm.py on an n x n mesh, fluid at rest."""
+    eq = ns.NavierStokesEquation(5000.0)
+    mesh = ns.Mesh([(-2.5, 2.5), (0.0, 4.0)], [5.0 / (n - 1), 4.0 / (n - 1)])
+    wall = ns.DirichletBoundaryCondition(
+        ns.vectorize_bc_function(lambda x, t: [0.0, 0.0, None, None]),
+        is_static=True,
+    )
+    inlet = ns.DirichletBoundaryCondition(
+        ns.vectorize_bc_function(lambda x, t: [1.0, 0.1, None, None]),
+        is_static=True,
+    )
+    cp = ns.ConstrainedProblem(eq, mesh, [(inlet, wall), (wall, wall)])
+    if d_t is None:
+        d_t = 0.1 * (4.0 / (n - 1)) ** 2 * 5000.0 / 4.0
+        d_t = min(d_t, 0.02 * 4.0 / (n - 1))
+    ic = ns.DiscreteInitialCondition(cp, np.zeros((n, n, 4)), True)
+    return ns.InitialValueProblem(cp, (0.0, n_steps * d_t), ic), d_t
+
+
 # name -> (builder, default vertices per axis, y_dim, spatial dims, label)
 WORKLOADS = {
     "burgers_3d": (burgers_problem, 512, 3, 3,
@@ -189,6 +214,9 @@ WORKLOADS = {
                             "ShallowWaterEquation(0.5) on a polar mesh, zero-flux height"),
     "diffusion_2d": (diffusion_2d_problem, 2048, 1, 2,
                      "DiffusionEquation(2), Dirichlet 1.5 / zero-flux boundaries"),
+    "navier_stokes_2d": (navier_stokes_problem, 4096, 4, 2,
+                         "NavierStokesEquation(Re=5000), inlet / no-slip walls, "
+                         "Jacobi stream-function solve capped per step"),
 }
 
 
@@ -494,6 +522,9 @@ def run_b200(args):
         total = args.warmup + args.steps
         ivp, d_t = builder(ns, n, total)
         op = FDMOperator(RK4(), ThreePointCentralDifferenceMethod(), d_t)
+        if args.workload == "navier_stokes_2d":
+            op.max_jacobi_sweeps = args.jacobi_sweeps
+            np.random.seed(0)
         cp, t, y0, low, plan = op.prepare(ivp)
         y_dev = dv.upload_state(y0, low.n_cells, low.y_dim)
         traj = torch.empty((total, y_dim * cells), dtype=torch.float64, device="cuda")
@@ -513,6 +544,11 @@ def run_b200(args):
         finite = bool(torch.isfinite(traj[-1]).all().item())
         value = cells * args.steps / (ms * 1e-3) / 1e9
         alg_bytes_step = 128 * y_dim * cells
+        sweeps = None
+        if op.last_jacobi_sweeps is not None:
+            # + 24 B per cell and Jacobi sweep
+            sweeps = float(np.mean(op.last_jacobi_sweeps))
+            alg_bytes_step += int(24 * sweeps * cells)
         achieved = alg_bytes_step * args.steps / (ms * 1e-3) / 1e9
         del traj, y_dev
         torch.cuda.empty_cache()
@@ -522,6 +558,8 @@ def run_b200(args):
         if not args.no_e2e:
             ivp_e, d_t_e = builder(ns, n, args.e2e_steps)
             op_e = FDMOperator(RK4(), ThreePointCentralDifferenceMethod(), d_t_e)
+            if args.workload == "navier_stokes_2d":
+                op_e.max_jacobi_sweeps = args.jacobi_sweeps
             op_e.solve(ivp_e)  # warm-up (pinned buffers, plan)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -541,7 +579,9 @@ def run_b200(args):
             }
             del sol
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and args.workload != "navier_stokes_2d":
+            # (the oracle's Jacobi solve iterates to tolerance: no bounded
+            # Navier-Stokes sample exists)
             cpu_n = args.cpu_grid if dims == 3 else 8 * args.cpu_grid
             v, secs = cpu_baseline(args.workload, cpu_n, 2)
             cpu = {
@@ -583,7 +623,8 @@ def run_b200(args):
                 "frac": achieved / peak,
                 "traffic": traffic,
                 "peak_source": peak_src,
-                "algorithmic_bytes_per_cell_step": 128 * y_dim,
+                "algorithmic_bytes_per_cell_step": alg_bytes_step // cells,
+                "jacobi_sweeps_per_step": sweeps,
                 "launches_per_step": launches // max(args.steps, 1),
             },
             "cpu_baseline": cpu,

@@ -836,10 +836,25 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
   }
 
   // loop-invariant part of the variant choice
-  const int path_a_in = pml_inplane_path(in_plane, i1, i2);
-  const int path_b_in = pml_inplane_path(owner, i1, i2);
+  const int path_a_in0 = pml_inplane_path(in_plane, i1, i2);
+  const int path_b_in0 = pml_inplane_path(owner, i1, i2);
 
+  // Per-thread loop invariants are passed through empty asm statements: the
+  // compiler then has to keep them in registers instead of re-deriving them
+  // from threadIdx / blockIdx in every iteration (dozens of instructions)
+  unsigned inv_flags = (in_plane ? 1u : 0u) | (owner ? 2u : 0u) |
+                       ((unsigned)path_a_in0 << 2) | ((unsigned)path_b_in0 << 4);
+  unsigned inv_coord = (unsigned)(i1 + 1) | ((unsigned)(i2 + 1) << 16);
+  int in_cell_o = in_cell, mid_cell_o = mid_cell, own_cell_o = own_cell;
+  asm volatile("" : "+r"(inv_flags), "+r"(inv_coord), "+r"(in_cell_o),
+               "+r"(mid_cell_o), "+r"(own_cell_o));
+  const int yr_cell_o = in_cell_o - PML_FHY * PML_IW;
   const i64 idx0 = pml_lin(0, in_plane ? i1 : 0, in_plane ? i2 : 0);
+  // stage B's outputs at this thread's cell, plane (iteration - 1): advanced
+  // by one plane per iteration
+  double* out_a =
+      (MODE == PML_F_RK4_12 ? b.u_out : b.y_next) + idx0 + (i64)(it0 - 1) * PmlAx<0>::S;
+  double* out_b = b.acc_out + idx0 + (i64)(it0 - 1) * PmlAx<0>::S;
   unsigned s_in = 0;   // input slot of plane i
   unsigned s_p = 0;    // pointwise slot / barrier of iteration i
   unsigned phase = 0;  // parity of the barrier's current use
@@ -858,40 +873,38 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
     // ---- stage B on plane i - 1 (tile cells), operands from the stage-A ring
     {
       const int z = i - 1;
-      const bool active = owner && z >= zb && z < ze;
-      const int path = (z > 0 && z < PML_N0 - 1) ? path_b_in : 0;
+      const bool active = (inv_flags & 2u) && z >= zb && z < ze;
+      const int path = (z > 0 && z < PML_N0 - 1) ? (int)((inv_flags >> 4) & 3u) : 0;
       if (active) {
         PmlCell c;
         c.i0 = z;
-        c.i1 = i1;
-        c.i2 = i2;
+        c.i1 = (int)(inv_coord & 0xffffu) - 1;
+        c.i2 = (int)(inv_coord >> 16) - 1;
         c.idx = idx0 + (i64)z * PmlAx<0>::S;
         PmlRingSrc<PML_MW, PML_MID_PLANE> src;
         src.y = a.y;
 #pragma unroll
         for (int d = -1; d <= 1; ++d)
-          src.base[d + 1] = mid_ring + (((z + d) & 3) * MID_SLOT) + mid_cell;
+          src.base[d + 1] = mid_ring + (((z + d) & 3) * MID_SLOT) + mid_cell_o;
         double K[NK];
         pml_eval_dt(path, b, src, c, b.t_eval, K);
-        const double* ar = acc_ring + s_p * ACC_SLOT + own_cell;
+        const double* ar = acc_ring + s_p * ACC_SLOT + own_cell_o;
 #pragma unroll
         for (int j = 0; j < PML_NDT; ++j) {
           const int k = PML_DT_IDX[j];
-          const i64 o = (i64)k * PML_NCELLS + c.idx;
+          const i64 o = (i64)k * PML_NCELLS;
           const double y0 = ys[j];
           if (MODE == PML_F_RK4_12) {
             const double kk = b.dt * K[j];
-            PML_ST(b.acc_out + o, ka[j] + 2.0 * kk);
-            PML_ST(b.u_out + o,
-                   pml_dirichlet(b.dir, k, c, y0 + kk / 2.0));
+            PML_ST(out_b + o, ka[j] + 2.0 * kk);
+            PML_ST(out_a + o, pml_dirichlet(b.dir, k, c, y0 + kk / 2.0));
           } else if (MODE == PML_F_RK4_34) {
             const double kk = b.dt * K[j];
             const double acc = ar[j * PML_OWN_PLANE] + 2.0 * ka[j];
-            PML_ST(b.y_next + o,
+            PML_ST(out_a + o,
                    pml_dirichlet(b.dir, k, c, y0 + pml_div6(acc + kk)));
           } else {
-            PML_ST(b.y_next + o,
-                   pml_dirichlet(b.dir, k, c, y0 + b.dt * K[j]));
+            PML_ST(out_a + o, pml_dirichlet(b.dir, k, c, y0 + b.dt * K[j]));
           }
         }
 #if PML_NALG + PML_NLAP > 0
@@ -909,24 +922,24 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
     // ---- stage A on plane i + 1 (tile + halo 1), operands from the input ring
     {
       const int z = i + 1;
-      const bool active = in_plane && z >= a_lo && z <= a_hi;
-      const int path = (z > 0 && z < PML_N0 - 1) ? path_a_in : 0;
+      const bool active = (inv_flags & 1u) && z >= a_lo && z <= a_hi;
+      const int path = (z > 0 && z < PML_N0 - 1) ? (int)((inv_flags >> 2) & 3u) : 0;
       if (active) {
         PmlCell c;
         c.i0 = z;
-        c.i1 = i1;
-        c.i2 = i2;
+        c.i1 = (int)(inv_coord & 0xffffu) - 1;
+        c.i2 = (int)(inv_coord >> 16) - 1;
         c.idx = idx0 + (i64)z * PmlAx<0>::S;
         PmlRingSrc<PML_IW, PML_IN_PLANE> src;
         src.y = a.y;
 #pragma unroll
         for (int d = 0; d < 3; ++d)
           src.base[d] =
-              in_ring + wrap(s_in + d, PML_FNS_IN) * IN_SLOT + in_cell;
+              in_ring + wrap(s_in + d, PML_FNS_IN) * IN_SLOT + in_cell_o;
         double K[NK];
         pml_eval_dt(path, a, src, c, a.t_eval, K);
-        double* slot = mid_ring + ((z & 3) * MID_SLOT) + mid_cell;
-        const double* yr = y_ring + s_p * YR_SLOT + yr_cell;
+        double* slot = mid_ring + ((z & 3) * MID_SLOT) + mid_cell_o;
+        const double* yr = y_ring + s_p * YR_SLOT + yr_cell_o;
 #pragma unroll
         for (int j = 0; j < PML_NDT; ++j) {
           const int k = PML_DT_IDX[j];
@@ -953,11 +966,13 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
                 a.dir, k, c, PML_LD(a.y + (i64)k * PML_NCELLS + c.idx));
           }
         }
-        if (first && owner && z >= zb && z < ze)
+        if (first && (inv_flags & 2u) && z >= zb && z < ze)
           pml_first_stage_extras(path, a, src, c);
 #endif
       }
     }
+    out_a += PmlAx<0>::S;
+    out_b += PmlAx<0>::S;
     s_in = wrap(s_in + 1, PML_FNS_IN);
     if (++s_p == PML_FNS_P) {
       s_p = 0;

@@ -169,10 +169,11 @@ def default_fused(shape, y_dim, n_dt=None, passthrough=False) -> Optional[FusedT
     elif nd == 3:
         # tile + halo 1 = 32 cells per row: one warp per row of the stage-A
         # tile (conflict-free shared-memory rows, warp-uniform row predicates);
-        # 8 rows + prefetch depth 1 let two thread blocks share an SM, so one
-        # computes while the other waits at its per-plane barrier (measured on
-        # B200, 512^3 Burgers RK4: 8.8 ms/step vs 9.3 for 30x16 at depth 2)
-        tx, ty = 30, 8
+        # 6 rows + prefetch depth 1: two thread blocks of 256 threads share an
+        # SM with 128 registers per thread, so one computes while the other
+        # waits at its per-plane barrier (measured on B200, 512^3 Burgers RK4:
+        # 7.9 ms/step; 30x8 at 96 registers 8.0-10.1, 30x16 one block 8.6-9.9)
+        tx, ty = 30, 6
     else:
         tx, ty = 222, 1
     if nd == 2:
