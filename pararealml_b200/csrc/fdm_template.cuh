@@ -1135,68 +1135,103 @@ extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ)
         a.dir, PML_LAP_IDX[j], c, y_init[c.idx * PML_NLAP + j]);
 }
 
-extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ)
-    pml_jacobi_sweep(const __grid_constant__ PmlJacobiArgs j) {
+// cell of repetition `rep`: every thread walks PML_JREP cells along axis 0, so
+// that their loads are in flight together and the block reduction is amortised
+__device__ __forceinline__ bool pml_jacobi_cell(PmlCell& c, int rep) {
+#if PML_NDIM <= 1
+  (void)rep;
+  return pml_this_cell(c);
+#elif PML_NDIM == 2
+  c.i1 = blockIdx.x * PML_BX + threadIdx.x;
+  c.i0 = (blockIdx.y * PML_JREP + rep) * PML_BY + threadIdx.y;
+  c.i2 = 0;
+  c.idx = pml_lin(c.i0, c.i1, 0);
+  return c.i1 < PML_N1 && c.i0 < PML_N0;
+#else
+  c.i2 = blockIdx.x * PML_BX + threadIdx.x;
+  c.i1 = blockIdx.y * PML_BY + threadIdx.y;
+  c.i0 = (blockIdx.z * PML_JREP + rep) * PML_BZ + threadIdx.z;
+  c.idx = pml_lin(c.i0, c.i1, c.i2);
+  return c.i2 < PML_N2 && c.i1 < PML_N1 && c.i0 < PML_N0;
+#endif
+}
+
+// one Jacobi update of one cell; IM as in the stencil primitives (interior
+// warps run without any boundary handling)
+template <int IM>
+__device__ __forceinline__ double pml_jacobi_cell_update(const PmlJacobiArgs& j,
+                                                         const PmlCell& c) {
   const PmlArgs& a = j.base;
-  if (*(const volatile int*)j.done) return;
-  PmlCell c;
-  const bool active = pml_this_cell(c);
   double sq = 0.0;
-  if (active) {
 #pragma unroll
-    for (int q = 0; q < PML_NLAP; ++q) {
-      const int comp = PML_LAP_IDX[q];
-      const double* p = j.y_hat + (i64)q * PML_NCELLS;
-      const PmlPlaneSrc ps{p};
-      double lo, hi, acc = 0.0;
+  for (int q = 0; q < PML_NLAP; ++q) {
+    const int comp = PML_LAP_IDX[q];
+    const double* p = j.y_hat + (i64)q * PML_NCELLS;
+    const PmlPlaneSrc ps{p};
+    double lo, hi, acc = 0.0;
 #if PML_COORD == 0
-      pml_nb2<0, 0>(a, ps, comp, c, lo, hi);
-      acc += (lo + hi) * PML_INVHH0;
+    pml_nb2<0, IM>(a, ps, comp, c, lo, hi);
+    acc += (lo + hi) * PML_INVHH0;
 #if PML_NDIM >= 2
-      pml_nb2<1, 0>(a, ps, comp, c, lo, hi);
-      acc += (lo + hi) * PML_INVHH1;
+    pml_nb2<1, IM>(a, ps, comp, c, lo, hi);
+    acc += (lo + hi) * PML_INVHH1;
 #endif
 #if PML_NDIM >= 3
-      pml_nb2<2, 0>(a, ps, comp, c, lo, hi);
-      acc += (lo + hi) * PML_INVHH2;
+    pml_nb2<2, IM>(a, ps, comp, c, lo, hi);
+    acc += (lo + hi) * PML_INVHH2;
 #endif
-      acc -= PML_LD(j.rhs + (i64)q * PML_NCELLS + c.idx);
-      const double v = acc * PML_JAC_INV_DIAG;
+    acc -= PML_LD(j.rhs + (i64)q * PML_NCELLS + c.idx);
+    const double v = acc * PML_JAC_INV_DIAG;
 #else
-      const double r = __ldg(a.coord[0] + c.i0);
-      const double r2 = r * r;
-      double diag;
-      pml_nb2<0, 0>(a, ps, comp, c, lo, hi);
+    const double r = __ldg(a.coord[0] + c.i0);
+    const double r2 = r * r;
+    double diag;
+    pml_nb2<0, IM>(a, ps, comp, c, lo, hi);
 #if PML_COORD == 3
-      const double s = __ldg(a.aux[1] + c.i2), co = __ldg(a.aux[2] + c.i2);
-      const double r2s2 = r2 * (s * s);
-      acc += (lo + hi) / (PML_H0 * PML_H0) + (hi - lo) / (PML_H0 * r);
-      pml_nb2<1, 0>(a, ps, comp, c, lo, hi);
-      acc += ((lo + hi) / (PML_H1 * PML_H1)) / r2s2;
-      pml_nb2<2, 0>(a, ps, comp, c, lo, hi);
-      acc += ((lo + hi) / (PML_H2 * PML_H2) +
-              co * (hi - lo) / (2.0 * PML_H2 * s)) / r2;
-      diag = 2.0 / (PML_H0 * PML_H0) + 2.0 / ((PML_H1 * PML_H1) * r2s2) +
-             2.0 / ((PML_H2 * PML_H2) * r2);
+    const double s = __ldg(a.aux[1] + c.i2), co = __ldg(a.aux[2] + c.i2);
+    const double r2s2 = r2 * (s * s);
+    acc += (lo + hi) / (PML_H0 * PML_H0) + (hi - lo) / (PML_H0 * r);
+    pml_nb2<1, IM>(a, ps, comp, c, lo, hi);
+    acc += ((lo + hi) / (PML_H1 * PML_H1)) / r2s2;
+    pml_nb2<2, IM>(a, ps, comp, c, lo, hi);
+    acc += ((lo + hi) / (PML_H2 * PML_H2) +
+            co * (hi - lo) / (2.0 * PML_H2 * s)) / r2;
+    diag = 2.0 / (PML_H0 * PML_H0) + 2.0 / ((PML_H1 * PML_H1) * r2s2) +
+           2.0 / ((PML_H2 * PML_H2) * r2);
 #else
-      acc += (lo + hi) / (PML_H0 * PML_H0) + (hi - lo) / (2.0 * PML_H0 * r);
-      pml_nb2<1, 0>(a, ps, comp, c, lo, hi);
-      acc += ((lo + hi) / (PML_H1 * PML_H1)) / r2;
-      diag = 2.0 / (PML_H0 * PML_H0) + 2.0 / ((PML_H1 * PML_H1) * r2);
+    acc += (lo + hi) / (PML_H0 * PML_H0) + (hi - lo) / (2.0 * PML_H0 * r);
+    pml_nb2<1, IM>(a, ps, comp, c, lo, hi);
+    acc += ((lo + hi) / (PML_H1 * PML_H1)) / r2;
+    diag = 2.0 / (PML_H0 * PML_H0) + 2.0 / ((PML_H1 * PML_H1) * r2);
 #if PML_COORD == 2
-      pml_nb2<2, 0>(a, ps, comp, c, lo, hi);
-      acc += (lo + hi) / (PML_H2 * PML_H2);
-      diag += 2.0 / (PML_H2 * PML_H2);
+    pml_nb2<2, IM>(a, ps, comp, c, lo, hi);
+    acc += (lo + hi) / (PML_H2 * PML_H2);
+    diag += 2.0 / (PML_H2 * PML_H2);
 #endif
 #endif
-      acc -= PML_LD(j.rhs + (i64)q * PML_NCELLS + c.idx);
-      const double v = acc / diag;
+    acc -= PML_LD(j.rhs + (i64)q * PML_NCELLS + c.idx);
+    const double v = acc / diag;
 #endif
-      const double vn = pml_dirichlet(a.dir, comp, c, v);
-      j.y_new[(i64)q * PML_NCELLS + c.idx] = vn;
-      const double d = vn - PML_LD(p + c.idx);
-      sq += d * d;
-    }
+    const double vn = pml_dirichlet(a.dir, comp, c, v);
+    j.y_new[(i64)q * PML_NCELLS + c.idx] = vn;
+    const double d = vn - PML_LD(p + c.idx);
+    sq += d * d;
+  }
+  return sq;
+}
+
+extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ)
+    pml_jacobi_sweep(const __grid_constant__ PmlJacobiArgs j) {
+  if (*(const volatile int*)j.done) return;
+  double sq = 0.0;
+#pragma unroll
+  for (int rep = 0; rep < (PML_NDIM <= 1 ? 1 : PML_JREP); ++rep) {
+    PmlCell c;
+    const bool active = pml_jacobi_cell(c, rep);
+    const int path = pml_warp_path(active, c);
+    if (active)
+      sq += path == 2 ? pml_jacobi_cell_update<PML_IM_ALL>(j, c)
+                      : pml_jacobi_cell_update<0>(j, c);
   }
   // deterministic block reduction of the squared update norm
   __shared__ double red[32];

@@ -96,6 +96,9 @@ std::string cu_err(CUresult r) {
     if (r_ != CUDA_SUCCESS) return fail(std::string(#call) + ": " + cu_err(r_)); \
   } while (0)
 
+// cells along axis 0 per thread of the Jacobi sweep (codegen.py JACOBI_REP)
+#define PML_JACOBI_REP 4
+
 // mirror of PmlArgs in fdm_template.cuh (kept layout-identical)
 struct PmlArgs {
   const double* u;
@@ -211,6 +214,7 @@ struct pml_plan {
   pml_tables tables{};
   dim3 grid, block;
   dim3 sgrid;  // grid of the stage kernels (zrep cells along axis 0 per thread)
+  dim3 jgrid;  // grid of the Jacobi sweep (PML_JACOBI_REP cells along axis 0)
   long long n_cells = 0;
   long long n_blocks = 0;
   long long launches = 0;
@@ -282,7 +286,7 @@ int jacobi_solve(pml_plan* p, const pml_workspace* ws, const PmlArgs& tbl,
   long long issued = 0;
   int host_flags[2] = {0, 0};
   long long batch = 16;
-  int n_partials = (int)p->n_blocks;
+  int n_partials = (int)((long long)p->jgrid.x * p->jgrid.y * p->jgrid.z);
   while (true) {
     long long todo = batch;
     if (max_sweeps > 0 && issued + todo > max_sweeps) todo = max_sweeps - issued;
@@ -296,7 +300,10 @@ int jacobi_solve(pml_plan* p, const pml_workspace* ws, const PmlArgs& tbl,
       j.partials = ws->partials;
       j.done = ws->flags;
       void* params[] = {&j};
-      if (launch(p, p->jac_sweep, params, s)) return -1;
+      PML_CU(g_drv.launchKernel(p->jac_sweep, p->jgrid.x, p->jgrid.y, p->jgrid.z,
+                                p->block.x, p->block.y, p->block.z, 0, s, params,
+                                nullptr));
+      p->launches += 1;
       const double* partials = ws->partials;
       int* done = ws->flags;
       int* sweeps = ws->flags + 1;
@@ -455,6 +462,11 @@ int pml_plan_create(const char* source, const pml_plan_desc* desc,
     p->sgrid.y = cdiv(n[0], b[1] * zrep);
   else if (desc->n_dims == 3)
     p->sgrid.z = cdiv(n[0], b[2] * zrep);
+  p->jgrid = p->grid;
+  if (desc->n_dims == 2)
+    p->jgrid.y = cdiv(n[0], b[1] * PML_JACOBI_REP);
+  else if (desc->n_dims == 3)
+    p->jgrid.z = cdiv(n[0], b[2] * PML_JACOBI_REP);
   p->n_cells = (long long)n[0] * n[1] * n[2];
   p->n_blocks = (long long)p->grid.x * p->grid.y * p->grid.z;
   *out = p;

@@ -105,6 +105,8 @@ def default_block(shape) -> Tuple[int, int, int]:
 
 
 N_SMS = 148
+#: cells along axis 0 per thread of the Jacobi sweep kernel (2-D / 3-D meshes)
+JACOBI_REP = 4
 SMALL_MESH_CELLS = 8192
 
 
@@ -175,7 +177,9 @@ def default_fused(shape, y_dim, n_dt=None, passthrough=False) -> Optional[FusedT
         # 7.9 ms/step; 30x8 at 96 registers 8.0-10.1, 30x16 one block 8.6-9.9)
         tx, ty = 30, 6
     else:
-        tx, ty = 222, 1
+        # measured on B200 (4096^2 polar shallow water RK4): 126 and 94 give
+        # 25.1 Gcell-steps/s, 222 gives 22.8, 446 gives 20.5
+        tx, ty = 126, 1
     if nd == 2:
         ty = 1
     tx = max(2, min(tx, shape[-1] + (shape[-1] % 2)))
@@ -579,6 +583,7 @@ def generate_source(spec: ProblemSpec) -> str:
         f"#define PML_F_THREADS {fused.threads if fused else 32}",
         f"#define PML_FMIN_BLOCKS {fused.min_blocks if fused else 1}",
         f"#define PML_ZREP {max(1, int(spec.zrep))}",
+        f"#define PML_JREP {JACOBI_REP}",
         f"#define PML_BX {block[0]}",
         f"#define PML_BY {block[1]}",
         f"#define PML_BZ {block[2]}",
