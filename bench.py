@@ -716,6 +716,9 @@ def run_b200(args):
                 "name": args.workload,
                 "grid": grid, "y_dim": y_dim, "d_t": d_t,
                 "parareal_iterations": iterations,
+                "parareal_update_norms": [
+                    [float(v) for v in row] for row in p.last_update_norms
+                ],
                 "cache": f"state ({cells * y_dim * 8 / 1e9:.2f} GB) is larger "
                          "than the 126 MB L2",
             },

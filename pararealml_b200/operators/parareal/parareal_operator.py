@@ -136,6 +136,9 @@ class PararealOperator(Operator):
         #: device planes of this rank's fine slice after the last solve
         #: (fast path) -- the sharded trajectory
         self.last_slice_trajectory = None
+        #: per iteration of the last solve (device path): the per-component
+        #: maximum over slices of the RMS end point update
+        self.last_update_norms = []
 
     # ------------------------------------------------------------------
     def _should_terminate(
@@ -370,6 +373,7 @@ class PararealOperator(Operator):
 
         have_fine = False
         self.last_iterations = 0
+        self.last_update_norms = []
         for i in range(min(size, self._max_iterations)):
             self.last_iterations += 1
             if not have_fine or rank >= i:
@@ -399,7 +403,9 @@ class PararealOperator(Operator):
                     world.send(u_end, rank + 1)
             worst = torch.sqrt(sumsq / n_cells)
             world.all_reduce_max(worst)
-            if bool(np.all(worst.cpu().numpy() < tol)):
+            worst_host = worst.cpu().numpy()
+            self.last_update_norms.append(worst_host.copy())
+            if bool(np.all(worst_host < tol)):
                 break
 
         shift_tmp = torch.empty(state, **f64)
