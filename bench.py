@@ -667,6 +667,11 @@ def run_b200(args):
     iterations = p.last_iterations
 
     e2e = None
+    # the timed solves' slice trajectory (slice_steps x 3.2 GB) must not stay
+    # resident next to the one the end-to-end solve allocates
+    p.last_slice_trajectory = None
+    del y0_planes
+    torch.cuda.empty_cache()
     if not args.no_e2e:
         # the reference's final Allgather would put the whole trajectory
         # (world x slice_steps x 3.2 GB) on every rank; the trajectory stays
