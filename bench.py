@@ -54,7 +54,7 @@ def parse_args():
     p.add_argument("--parareal-tol", type=float, default=1e-6,
                    help="RMS end point update tolerance (states are O(1))")
     p.add_argument("--cpu-grid", type=int, default=96)
-    p.add_argument("--cpu-parareal-grid", type=int, default=48,
+    p.add_argument("--cpu-parareal-grid", type=int, default=32,
                    help="vertices per axis of the host-process Parareal sample")
     p.add_argument("--jacobi-sweeps", type=int, default=100,
                    help="cap on Jacobi sweeps per step (navier_stokes_2d; the "

@@ -113,3 +113,59 @@ def test_product_path_fails_loudly_without_a_gpu():
     op = FDMOperator(RK4(), ThreePointCentralDifferenceMethod(), case.d_t)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         op.solve(case.build(ns))
+
+
+@pytest.mark.parametrize(
+    "shape,y_dim",
+    [((512, 512, 512), 3), ((64, 48, 40), 1), ((4096, 4096), 3), ((150, 600), 1),
+     ((20, 21, 22), 6), ((9, 9, 4), 2)],
+)
+def test_fused_tile_fits_the_hardware(shape, y_dim, monkeypatch):
+    """Geometry of the fused stage-pair kernels: thread, TMA box and shared
+    memory limits of sm_100a hold for every mesh the default rule accepts."""
+    for key in ("PML_FUSE", "PML_FTILE", "PML_FDEPTH", "PML_FZC", "PML_FMIN_BLOCKS"):
+        monkeypatch.delenv(key, raising=False)
+    tile = codegen.default_fused(shape, y_dim, y_dim, False)
+    assert tile is not None
+    hy = 1 if len(shape) == 3 else 0
+    assert tile.tx % 2 == 0 and tile.tx + 4 <= 256
+    assert (tile.tx + 2) * (tile.ty + 2 * hy) <= tile.threads <= 1024
+    assert tile.threads % 32 == 0
+    assert tile.smem_first <= tile.smem_pointwise <= 227 * 1024 - 2048
+    assert tile.min_blocks * (tile.smem_pointwise + 1024) <= 228 * 1024
+    assert tile.min_blocks * tile.threads * 96 <= 65536 or tile.min_blocks == 1
+    assert 1 <= tile.zc <= shape[0]
+
+
+def test_fused_pairs_are_skipped_where_they_do_not_apply(monkeypatch):
+    monkeypatch.delenv("PML_FUSE", raising=False)
+    # odd contiguous extent (TMA rows start on 16-byte boundaries), 1-D meshes,
+    # systems with algebraic components
+    assert codegen.default_fused((21, 21), 1, 1, False) is None
+    assert codegen.default_fused((101,), 1, 1, False) is None
+    assert codegen.default_fused((64, 64, 64), 2, 1, True) is None
+    monkeypatch.setenv("PML_FUSE", "0")
+    assert codegen.default_fused((64, 64, 64), 3, 3, False) is None
+
+
+def test_nvrtc_compiles_the_fused_pair_kernels(tmp_path, monkeypatch):
+    """TMA (UTMALDG) and mbarrier (SYNCS) code paths build for sm_100a."""
+    import subprocess
+
+    monkeypatch.delenv("PML_FUSE", raising=False)
+    monkeypatch.setenv("PML_SMALL", "0")
+    eq = ns.BurgersEquation(3, 100.0)
+    mesh = ns.Mesh([(0.0, 1.0)] * 3, [1.0 / 39, 1.0 / 47, 1.0 / 63])
+    bc = ns.NeumannBoundaryCondition(lambda x, t: np.zeros((len(x), 3)), is_static=True)
+    cp = ns.ConstrainedProblem(eq, mesh, [(bc, bc)] * 3)
+    low = lower_problem(cp)
+    spec = low.spec(**plan_overrides(cp, low, None))
+    assert spec.fused is not None
+    src = codegen.generate_source(spec)
+    out = str(tmp_path / "fused.cubin")
+    _native.compile_to_cubin(src, out)
+    sass = subprocess.run(
+        ["cuobjdump", "-sass", out], capture_output=True, text=True
+    ).stdout
+    assert "pml_fused_rk4_12" in sass and "pml_fused_rk4_34" in sass
+    assert "UTMALDG" in sass and "SYNCS" in sass
