@@ -303,6 +303,9 @@ class PararealOperator(Operator):
 
         if world is None:
             world = _World()
+        # the previous solve's slice trajectory must not stay resident next
+        # to the one allocated below
+        self.last_slice_trajectory = None
         f, g = self._f, self._g
         cp = ivp.constrained_problem
         t0, t1 = ivp.t_interval
