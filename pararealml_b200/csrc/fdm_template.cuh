@@ -615,22 +615,17 @@ enum { PML_F_RK4_12 = 0, PML_F_RK4_34 = 1, PML_F_MID = 2 };
 __device__ __forceinline__ unsigned pml_smem_addr(const void* p) {
   return (unsigned)__cvta_generic_to_shared(p);
 }
-__device__ __forceinline__ void pml_mbar_init(unsigned long long* bar,
-                                              unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pml_smem_addr(bar)),
-               "r"(count)
+// (barriers are addressed by their 32-bit shared-memory address, computed once)
+__device__ __forceinline__ void pml_mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)
                : "memory");
 }
-__device__ __forceinline__ void pml_mbar_expect_tx(unsigned long long* bar,
-                                                   unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
-                   pml_smem_addr(bar)),
+__device__ __forceinline__ void pml_mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
                "r"(bytes)
                : "memory");
 }
-__device__ __forceinline__ void pml_mbar_wait(unsigned long long* bar,
-                                              unsigned parity) {
-  const unsigned addr = pml_smem_addr(bar);
+__device__ __forceinline__ void pml_mbar_wait(unsigned addr, unsigned parity) {
   unsigned ok;
   do {
     asm volatile(
@@ -649,12 +644,11 @@ __device__ __forceinline__ void pml_mbar_wait(unsigned long long* bar,
 // signalled on the mbarrier
 __device__ __forceinline__ void pml_tma_box(unsigned dst, const void* tmap,
                                             int x, int y, int z, int comp,
-                                            unsigned long long* bar) {
+                                            unsigned bar) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::"
       "complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
-      "l"((unsigned long long)tmap), "r"(x), "r"(y), "r"(z), "r"(comp),
-      "r"(pml_smem_addr(bar))
+      "l"((unsigned long long)tmap), "r"(x), "r"(y), "r"(z), "r"(comp), "r"(bar)
       : "memory");
 }
 
@@ -726,6 +720,10 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
   const int a_lo = max(zb - 1, 0), a_hi = min(ze, PML_N0 - 1);
   const int in_lo = max(zb - 2, 0), in_hi = min(ze + 1, PML_N0 - 1);
   const int it0 = a_lo - 1, it1 = ze;  // iterations: A(i + 1) and B(i - 1)
+  // shared-memory address of the barriers (kept in a register: re-deriving it
+  // reads a special register in every iteration)
+  unsigned bars_s = pml_smem_addr(bars);
+  asm volatile("" : "+r"(bars_s));
 
   // ---- this thread's TMA box (at most one): one component plane of the
   // input tile, of the step-start state or of the accumulator.  Boxes are dealt
@@ -787,7 +785,7 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
   // (stage A) and accumulator plane j - 1 (stage B); sp = pointwise slot of j,
   // si = input slot of plane j + 2
   auto fetch = [&](int j, int n_in, unsigned si, unsigned sp) {
-    unsigned long long* bar = bars + sp;
+    const unsigned bar = bars_s + sp * 8u;
     if (tid == 0) {
       unsigned tx = 0;
       for (int p = j + 3 - n_in; p <= j + 2; ++p)
@@ -817,7 +815,7 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
 
   if (tid == 0) {
 #pragma unroll
-    for (int k = 0; k < PML_FNS_P; ++k) pml_mbar_init(bars + k, 1);
+    for (int k = 0; k < PML_FNS_P; ++k) pml_mbar_init(bars_s + k * 8u, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -869,7 +867,7 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
     if (i + PML_FDEPTH <= it1)
       fetch(i + PML_FDEPTH, 1, wrap(s_in + PML_FDEPTH + 2, PML_FNS_IN),
             wrap(s_p + PML_FDEPTH, PML_FNS_P));
-    pml_mbar_wait(bars + s_p, phase);
+    pml_mbar_wait(bars_s + s_p * 8u, phase);
     // ---- stage B on plane i - 1 (tile cells), operands from the stage-A ring
     {
       const int z = i - 1;

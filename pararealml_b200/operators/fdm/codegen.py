@@ -171,10 +171,11 @@ def default_fused(shape, y_dim, n_dt=None, passthrough=False) -> Optional[FusedT
     elif nd == 3:
         # tile + halo 1 = 32 cells per row: one warp per row of the stage-A
         # tile (conflict-free shared-memory rows, warp-uniform row predicates);
-        # 6 rows + prefetch depth 1: two thread blocks of 256 threads share an
+        # 6 rows + prefetch depth 2: two thread blocks of 256 threads share an
         # SM with 128 registers per thread, so one computes while the other
         # waits at its per-plane barrier (measured on B200, 512^3 Burgers RK4:
-        # 7.9 ms/step; 30x8 at 96 registers 8.0-10.1, 30x16 one block 8.6-9.9)
+        # 7.6 ms/step; depth 1 7.9, 30x8 at 96 registers 8.0-10.1, 30x16 with
+        # one block per SM 8.6-9.9)
         tx, ty = 30, 6
     else:
         # measured on B200 (4096^2 polar shallow water RK4): 126 and 94 give
@@ -186,7 +187,7 @@ def default_fused(shape, y_dim, n_dt=None, passthrough=False) -> Optional[FusedT
     tx -= tx % 2
     if nd == 3:
         ty = max(1, min(ty, shape[1]))
-    depth = int(os.environ.get("PML_FDEPTH", "1" if nd == 3 else "2"))
+    depth = int(os.environ.get("PML_FDEPTH", "2"))
     n_ring = n_dt if passthrough else y_dim
     hy = 1 if nd == 3 else 0
 
