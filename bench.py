@@ -579,6 +579,24 @@ def run_b200(args):
                         "Solution",
             }
             del sol
+            # the same solve with the trajectory left in HBM (lazy Solution):
+            # only the final state is read back
+            op_e.device_resident_solution = True
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            sol = op_e.solve(ivp_e)
+            last = sol.device_trajectory[-1].cpu()
+            dt_l = time.perf_counter() - t0
+            e2e["device_resident"] = {
+                "value": cells * args.e2e_steps / dt_l / 1e9,
+                "unit": UNIT,
+                "h2d_bytes_per_step": state_bytes // args.e2e_steps,
+                "d2h_bytes_per_step": state_bytes // args.e2e_steps,
+                "note": "FDMOperator.device_resident_solution = True: the "
+                        "trajectory stays in HBM behind a lazy Solution, only "
+                        "the final state is copied to the host",
+            }
+            del sol, last
         cpu = None
         if not args.no_cpu_baseline and args.workload != "navier_stokes_2d":
             # (the oracle's Jacobi solve iterates to tolerance: no bounded
@@ -592,7 +610,9 @@ def run_b200(args):
                           f"2 steps, {secs:.1f} s, single process "
                           f"({os.cpu_count()} host cores present)",
             }
-        traffic = load_traffic().get(f"{args.workload}_{n}_rk4_step_dram_bytes")
+        profile = load_traffic()
+        traffic = profile.get(f"{args.workload}_{n}_rk4_step_dram_bytes")
+        kernels = profile.get(f"{args.workload}_{n}_kernels")
         line = {
             "metric": metric_name(args.workload, n),
             "value": value,
@@ -626,6 +646,11 @@ def run_b200(args):
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_cell_step": alg_bytes_step // cells,
                 "jacobi_sweeps_per_step": sweeps,
+                "scope": "one time step = all stage(-pair) launches of the "
+                         "timed region; achieved = algorithmic bytes of a step "
+                         "/ step time, traffic = measured DRAM bytes of a step "
+                         "(ncu, profiles/traffic.json)",
+                "kernels_ncu": kernels,
                 "launches_per_step": launches // max(args.steps, 1),
             },
             "cpu_baseline": cpu,

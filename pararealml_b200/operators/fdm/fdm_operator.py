@@ -107,6 +107,10 @@ class FDMOperator(Operator):
         #: optional cap on Jacobi sweeps per step (0 = run to tolerance as the
         #: reference does)
         self.max_jacobi_sweeps = 0
+        #: extension: keep the whole trajectory
+        #: in HBM and copy it to the host only when the returned ``Solution``
+        #: is read; its component planes are ``solution.device_trajectory``
+        self.device_resident_solution = False
 
     # ------------------------------------------------------------------
     # plan selection
@@ -210,7 +214,38 @@ class FDMOperator(Operator):
     # ------------------------------------------------------------------
     # the drop-in entry point
     # ------------------------------------------------------------------
+    def _solve_lazily(self, ivp) -> Solution:
+        """The trajectory stays on the device as component planes
+        ``(n_steps, y_dim * n_cells)``; reading the ``Solution`` converts it
+        to the reference's channels-last layout and copies it to the host in
+        chunks through pinned memory."""
+        cp = ivp.constrained_problem
+        t, traj = self.solve_on_device(ivp)
+        low = lowered(cp)
+        n_steps, state = traj.shape
+        y_shape = tuple(cp.y_vertices_shape)
+
+        def materialise() -> np.ndarray:
+            host = torch.empty((n_steps, state), dtype=torch.float64, pin_memory=True)
+            chunk = max(1, min(n_steps, (1 << 30) // (state * 8)))
+            need_stage = low.y_dim > 1 and low.n_cells > 1
+            for first in range(0, n_steps, chunk):
+                part = traj[first : first + chunk]
+                if need_stage:
+                    part = dv.soa_to_aos(part, low.n_cells, low.y_dim, part.shape[0])
+                host[first : first + part.shape[0]].copy_(part, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return host.numpy().reshape((n_steps,) + y_shape)
+
+        sol = Solution(
+            ivp, t, materialise, vertex_oriented=True, d_t=self._d_t, copy=False
+        )
+        sol.device_trajectory = traj
+        return sol
+
     def solve(self, ivp, parallel_enabled: bool = True) -> Solution:
+        if self.device_resident_solution:
+            return self._solve_lazily(ivp)
         cp, t, y0, low, plan = self.prepare(ivp)
         n_steps = len(t) - 1
         state = low.y_dim * low.n_cells

@@ -122,6 +122,25 @@ def test_solve_on_device_keeps_the_trajectory_in_hbm():
     assert per_step_rel_err(y[g["steps"]], g["y"]) <= 1e-12
 
 
+def test_device_resident_solution_is_read_lazily():
+    """the trajectory stays in HBM until the
+    Solution is read; values equal the eager path's."""
+    import torch
+
+    case = cases.FDM_BY_NAME["shallow_water_polar_rk4"]
+    ivp = case.build(ns)
+    eager = make_operator(case).solve(ivp).discrete_y()
+    op = make_operator(case)
+    op.device_resident_solution = True
+    sol = op.solve(ivp)
+    assert sol.device_trajectory.is_cuda
+    assert sol.device_trajectory.shape == (len(eager), eager[0].size)
+    assert sol._y is None  # nothing copied yet
+    assert np.array_equal(sol.discrete_y(), eager)
+    g = load_golden(case.name)
+    assert per_step_rel_err(sol.discrete_y()[g["steps"]], g["y"]) <= 1e-12
+
+
 @pytest.mark.parametrize(
     "case_name",
     ["diffusion_2d_rk4", "wave_2d_dynamic_mid", "cahn_hilliard_3d_rk4",
