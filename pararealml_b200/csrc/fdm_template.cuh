@@ -403,6 +403,23 @@ __device__ __forceinline__ void pml_stage_cell(const PmlArgs& a, bool active,
   }
   const PmlGlobalSrc src{P};
 
+  // the pointwise operands (step-start value, accumulator) are requested
+  // before the right-hand side is evaluated, so that they travel together with
+  // the stencil loads instead of in a second, dependent round trip to DRAM
+  // (systems with few time-stepped components: the registers are there)
+  constexpr bool early = PML_NDT <= 2;
+  constexpr bool uses_acc =
+      STAGE == PML_RK4_2 || STAGE == PML_RK4_3 || STAGE == PML_RK4_4;
+  double y_early[PML_NDT > 0 ? PML_NDT : 1], acc_early[PML_NDT > 0 ? PML_NDT : 1];
+  if (early) {
+#pragma unroll
+    for (int j = 0; j < PML_NDT; ++j) {
+      const i64 o = (i64)PML_DT_IDX[j] * PML_NCELLS + c.idx;
+      y_early[j] = first ? PML_LD(P[PML_DT_IDX[j]] + c.idx) : PML_LD_ONCE(a.y + o);
+      acc_early[j] = uses_acc ? PML_LD_ONCE(a.acc_in + o) : 0.0;
+    }
+  }
+
   double K[PML_NDT > 0 ? PML_NDT : 1];
   pml_eval_dt(path, a, src, c, a.t_eval, K);
 
@@ -410,7 +427,8 @@ __device__ __forceinline__ void pml_stage_cell(const PmlArgs& a, bool active,
   for (int j = 0; j < PML_NDT; ++j) {
     const int k = PML_DT_IDX[j];
     const i64 o = (i64)k * PML_NCELLS + c.idx;
-    const double y0 = first ? PML_LD(P[k] + c.idx) : PML_LD_ONCE(a.y + o);
+    const double y0 = early ? y_early[j]
+                            : (first ? PML_LD(P[k] + c.idx) : PML_LD_ONCE(a.y + o));
     if (STAGE == PML_FE) {
       PML_ST(a.y_next + o, pml_dirichlet(a.dir, k, c, y0 + a.dt * K[j]));
     } else if (STAGE == PML_MID1) {
@@ -423,15 +441,16 @@ __device__ __forceinline__ void pml_stage_cell(const PmlArgs& a, bool active,
         PML_ST(a.acc_out + o, kk);
         PML_ST(a.u_out + o, pml_dirichlet(a.dir, k, c, y0 + kk / 2.0));
       } else if (STAGE == PML_RK4_2) {
-        PML_ST(a.acc_out + o, PML_LD_ONCE(a.acc_in + o) + 2.0 * kk);
+        const double ac = early ? acc_early[j] : PML_LD_ONCE(a.acc_in + o);
+        PML_ST(a.acc_out + o, ac + 2.0 * kk);
         PML_ST(a.u_out + o, pml_dirichlet(a.dir, k, c, y0 + kk / 2.0));
       } else if (STAGE == PML_RK4_3) {
-        PML_ST(a.acc_out + o, PML_LD_ONCE(a.acc_in + o) + 2.0 * kk);
+        const double ac = early ? acc_early[j] : PML_LD_ONCE(a.acc_in + o);
+        PML_ST(a.acc_out + o, ac + 2.0 * kk);
         PML_ST(a.u_out + o, pml_dirichlet(a.dir, k, c, y0 + kk));
       } else {
-        PML_ST(a.y_next + o,
-               pml_dirichlet(a.dir, k, c,
-                             y0 + pml_div6(PML_LD_ONCE(a.acc_in + o) + kk)));
+        const double ac = early ? acc_early[j] : PML_LD_ONCE(a.acc_in + o);
+        PML_ST(a.y_next + o, pml_dirichlet(a.dir, k, c, y0 + pml_div6(ac + kk)));
       }
     }
   }
