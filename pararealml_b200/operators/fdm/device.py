@@ -313,8 +313,41 @@ def soa_to_aos(soa: torch.Tensor, n_cells: int, y_dim: int, n_states: int = 1,
     return out
 
 
+#: pinned staging buffers for large host -> device uploads (two, reused)
+_UPLOAD_STAGE = []
+_UPLOAD_CHUNK = 1 << 25  # doubles (256 MiB)
+
+
+def _to_device_staged(flat: torch.Tensor, dev: torch.device) -> torch.Tensor:
+    """Pageable host tensor -> device through two pinned staging buffers: the
+    (multi-threaded) host copy of one chunk overlaps the DMA of the previous
+    one.  A plain ``.to(device)`` of pageable memory runs at ~11 GB/s on the
+    B200 boxes, this at the speed of the host copy (PCIe gen5 x16 does 55)."""
+    n = flat.numel()
+    if n <= _UPLOAD_CHUNK:
+        return flat.to(dev, non_blocking=True)
+    while len(_UPLOAD_STAGE) < 2:
+        _UPLOAD_STAGE.append(
+            (torch.empty(_UPLOAD_CHUNK, dtype=torch.float64, pin_memory=True),
+             torch.cuda.Event())
+        )
+    out = torch.empty(n, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream()
+    for k, first in enumerate(range(0, n, _UPLOAD_CHUNK)):
+        stage, done = _UPLOAD_STAGE[k % 2]
+        if k >= 2:
+            done.synchronize()  # the DMA out of this buffer has finished
+        m = min(_UPLOAD_CHUNK, n - first)
+        stage[:m].copy_(flat[first : first + m])
+        out[first : first + m].copy_(stage[:m], non_blocking=True)
+        done.record(stream)
+    for _, done in _UPLOAD_STAGE:
+        done.synchronize()  # the buffers may be reused by the next upload
+    return out
+
+
 def upload_state(y: np.ndarray, n_cells: int, y_dim: int) -> torch.Tensor:
     """Channels-last host state -> component planes on the device."""
     dev = require_cuda()
     flat = _from_numpy(np.ascontiguousarray(y, dtype=np.float64).reshape(-1))
-    return aos_to_soa(flat.to(dev, non_blocking=True), n_cells, y_dim)
+    return aos_to_soa(_to_device_staged(flat, dev), n_cells, y_dim)

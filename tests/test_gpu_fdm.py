@@ -122,6 +122,20 @@ def test_solve_on_device_keeps_the_trajectory_in_hbm():
     assert per_step_rel_err(y[g["steps"]], g["y"]) <= 1e-12
 
 
+def test_staged_upload_of_large_states(monkeypatch):
+    """Large initial states go to the device through two pinned staging
+    buffers (chunked, overlapped with the DMA); forced here with tiny chunks."""
+    from pararealml_b200.operators.fdm import device as dv
+
+    monkeypatch.setattr(dv, "_UPLOAD_CHUNK", 1000)
+    monkeypatch.setattr(dv, "_UPLOAD_STAGE", [])
+    rng = np.random.default_rng(1)
+    y = rng.normal(size=(17, 19, 23, 3))
+    planes = dv.upload_state(y, 17 * 19 * 23, 3).cpu().numpy()
+    expected = np.moveaxis(y.reshape(-1, 3), 1, 0).reshape(-1)
+    assert np.array_equal(planes, expected)
+
+
 def test_device_resident_solution_is_read_lazily():
     """the trajectory stays in HBM until the
     Solution is read; values equal the eager path's."""
