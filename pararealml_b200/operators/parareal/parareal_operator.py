@@ -393,7 +393,10 @@ class PararealOperator(Operator):
                 if rank > i:
                     world.recv(u_start, rank - 1)
                     g.integrate_on_device(cp, g_plan, u_start, t_gs, g_slice)
-                    g_end.copy_(g_slice[-1])
+                    # the coarse end point is read in place (the slice buffer
+                    # is only rewritten by the next coarse solve, after the
+                    # next correction has been formed)
+                    g_end = g_slice[-1]
                 _native.check(
                     lib.pml_parareal_update(
                         g_end.data_ptr(), corr.data_ptr(), u_end.data_ptr(),
