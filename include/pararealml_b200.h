@@ -90,6 +90,19 @@ int pml_fdm_run(pml_plan* plan, int integrator, const pml_workspace* ws,
                 double jacobi_tol, long long max_sweeps, int* sweeps_out_host,
                 void* stream);
 
+/* The same time step one launch ("phase") at a time, for callers that
+ * decompose the mesh into slabs of axis 0 and exchange halo planes between
+ * launches (fully time-stepped systems only).  pml_fdm_phase_count: launches
+ * per step (RK4: 2 stage-pair launches, or 4 stage launches).  pml_fdm_phase
+ * runs phase `phase` of the step starting at t; *fresh_out_dev receives the
+ * device buffer that phase has written -- the next phase's stencil input
+ * (workspace memory) or y_next_dev after the last phase. */
+int pml_fdm_phase_count(const pml_plan* plan, int integrator);
+int pml_fdm_phase(pml_plan* plan, int integrator, const pml_workspace* ws,
+                  const double* y_dev, double* y_next_dev, double t, double d_t,
+                  long long slot0, int phase, double** fresh_out_dev,
+                  void* stream);
+
 /* One evaluation of the generated right-hand sides (differentiator entry
  * points, numerical_differentiator.py:114-870). */
 int pml_eval_rhs(pml_plan* plan, const double* u_dev, double* out_dev, double t,

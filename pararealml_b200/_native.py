@@ -87,6 +87,14 @@ SYMBOLS = {
             c_void_p, c_double, c_longlong, POINTER(c_int), c_void_p,
         ],
     ),
+    "pml_fdm_phase_count": (c_int, [c_void_p, c_int]),
+    "pml_fdm_phase": (
+        c_int,
+        [
+            c_void_p, c_int, POINTER(Workspace), c_void_p, c_void_p, c_double,
+            c_double, c_longlong, c_int, POINTER(c_void_p), c_void_p,
+        ],
+    ),
     "pml_eval_rhs": (
         c_int, [c_void_p, c_void_p, c_void_p, c_double, c_longlong, c_void_p]
     ),

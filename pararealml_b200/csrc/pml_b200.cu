@@ -325,6 +325,108 @@ int jacobi_solve(pml_plan* p, const pml_workspace* ws, const PmlArgs& tbl,
   return launch(p, p->jac_store, params, s);
 }
 
+// One explicit time step y -> y_next as a sequence of launches ("phases").
+// phase < 0 runs all of them; otherwise only that one, and *fresh receives the
+// buffer it has written: the next phase's stencil input, or y_next after the
+// last phase (a domain-decomposed caller exchanges its halo planes then).
+int run_step(pml_plan* p, int integrator, const pml_workspace* ws, PmlArgs& a,
+             const double* y, double* y_next, double t, double d_t,
+             long long s_t, int phase, double** fresh, CUstream s) {
+  const double half = d_t / 2.0;
+  const long long s_h = s_t + 1, s_f = s_t + 2;
+  a.y = y;
+  a.y_next = y_next;
+  bind_dir(p, a.dir_full, s_f);
+  void* params[] = {&a};
+  int index = 0;  // phase counter
+  auto wanted = [&](double* written) {
+    const bool run = phase < 0 || phase == index;
+    if (run && fresh) *fresh = written;
+    ++index;
+    return run;
+  };
+  auto stage = [&](int k, const double* u, double* u_out, double t_eval,
+                   long long neu_slot, long long dir_slot) {
+    if (!wanted(u_out ? u_out : y_next)) return 0;
+    a.u = u;
+    a.u_out = u_out;
+    a.acc_in = ws->acc;
+    a.acc_out = ws->acc;
+    a.t_eval = t_eval;
+    bind_neu(p, a.neu, neu_slot);
+    bind_dir(p, a.dir, dir_slot);
+    CUresult r_ = g_drv.launchKernel(p->stage[k], p->sgrid.x, p->sgrid.y,
+                                     p->sgrid.z, p->block.x, p->block.y,
+                                     p->block.z, 0, s, params, nullptr);
+    if (r_ != CUDA_SUCCESS) return fail("stage launch: " + cu_err(r_));
+    p->launches += 1;
+    return 0;
+  };
+  auto fused = [&](int k, const double* u, double* u_out, double t_a,
+                   long long neu_a, long long dir_a, double t_b,
+                   long long neu_b, long long dir_b) {
+    if (!wanted(u_out ? u_out : y_next)) return 0;
+    PmlFusedArgs f;
+    std::memset(&f, 0, sizeof(f));
+    const unsigned ftx = (unsigned)p->desc.fused_tile[0];
+    const unsigned fty = (unsigned)p->desc.fused_tile[1];
+    const unsigned hy = p->desc.n_dims == 3 ? 1u : 0u;
+    // stage A's stencil input (tile + halo 2); for stages 3+4 also the
+    // step-start state (rows of the stage-A tile) and the accumulator
+    if (state_tensor_map(p, u, ftx + 4, fty + 4 * hy, &f.tm_in)) return -1;
+    if (k == 1) {
+      if (state_tensor_map(p, y, ftx + 4, fty + 2 * hy, &f.tm_y)) return -1;
+      if (state_tensor_map(p, ws->acc, ftx, fty, &f.tm_acc)) return -1;
+    }
+    a.u = u;
+    a.u_out = u_out;
+    a.acc_in = ws->acc;
+    a.acc_out = ws->acc;
+    a.t_eval = t_a;
+    bind_neu(p, a.neu, neu_a);
+    bind_dir(p, a.dir, dir_a);
+    f.s = a;
+    f.t_eval_b = t_b;
+    bind_neu(p, f.neu_b, neu_b);
+    bind_dir(p, f.dir_b, dir_b);
+    void* fparams[] = {&f};
+    CUresult r_ = g_drv.launchKernel(p->fused[k], p->fgrid.x, p->fgrid.y,
+                                     p->fgrid.z, p->fblock.x, p->fblock.y, 1,
+                                     p->fsmem[k], s, fparams, nullptr);
+    if (r_ != CUDA_SUCCESS) return fail("fused launch: " + cu_err(r_));
+    p->launches += 1;
+    return 0;
+  };
+  int rc = 0;
+  // the fused kernels move boxes with the TMA unit: 16-byte aligned planes.
+  // (phase-wise callers get the fused sequence whenever the plan has it: the
+  // number of phases must not depend on pointer values)
+  auto aligned = [](const void* q) { return ((uintptr_t)q & 15u) == 0; };
+  const bool all_aligned = aligned(y) && aligned(y_next) && aligned(ws->u_b) &&
+                           aligned(ws->acc);
+  if (p->desc.fused && phase >= 0 && !all_aligned)
+    return fail("phase-wise stepping needs 16-byte aligned states");
+  const bool use_fused = p->desc.fused && all_aligned;
+  if (integrator == PML_INTEGRATOR_FORWARD_EULER) {
+    rc = stage(0, y, nullptr, t, s_t, s_f);
+  } else if (use_fused && integrator == PML_INTEGRATOR_EXPLICIT_MIDPOINT) {
+    rc = fused(2, y, nullptr, t, s_t, s_h, t + half, s_h, s_f);
+  } else if (use_fused) {
+    // RK4: stages 1+2 write u_b (= u3) and acc; stages 3+4 write the slot
+    rc = fused(0, y, ws->u_b, t, s_t, s_h, t + half, s_h, s_h);
+    if (!rc) rc = fused(1, ws->u_b, nullptr, t + half, s_h, s_f, t + d_t, s_f, s_f);
+  } else if (integrator == PML_INTEGRATOR_EXPLICIT_MIDPOINT) {
+    rc = stage(1, y, ws->u_a, t, s_t, s_h);
+    if (!rc) rc = stage(2, ws->u_a, nullptr, t + half, s_h, s_f);
+  } else {
+    rc = stage(3, y, ws->u_a, t, s_t, s_h);
+    if (!rc) rc = stage(4, ws->u_a, ws->u_b, t + half, s_h, s_h);
+    if (!rc) rc = stage(5, ws->u_b, ws->u_a, t + half, s_h, s_f);
+    if (!rc) rc = stage(6, ws->u_a, nullptr, t + d_t, s_f, s_f);
+  }
+  return rc;
+}
+
 }  // namespace
 
 extern "C" {
@@ -503,7 +605,6 @@ int pml_fdm_run(pml_plan* p, int integrator, const pml_workspace* ws,
   fill_tables(p, a);
   a.dt = d_t;
   a.lap_rhs = ws->lap_rhs;
-  const double half = d_t / 2.0;
   const long long lap_elems = (long long)p->desc.n_lap * p->n_cells;
   if (p->small_run && p->desc.n_lap == 0 && ws->t_dev && ws->t_capacity > 0) {
     // small mesh: all steps of a chunk in one single-block launch
@@ -542,84 +643,9 @@ int pml_fdm_run(pml_plan* p, int integrator, const pml_workspace* ws,
     const double t = t_host[j];
     const double* y = j == 0 ? y0 : traj + (long long)(j - 1) * stride;
     double* y_next = traj + (long long)j * stride;
-    const long long s_t = slot0 + 3LL * j, s_h = s_t + 1, s_f = s_t + 2;
-    a.y = y;
-    a.y_next = y_next;
-    bind_dir(p, a.dir_full, s_f);
-    void* params[] = {&a};
-    auto stage = [&](int k, const double* u, double* u_out, double t_eval,
-                     long long neu_slot, long long dir_slot) {
-      a.u = u;
-      a.u_out = u_out;
-      a.acc_in = ws->acc;
-      a.acc_out = ws->acc;
-      a.t_eval = t_eval;
-      bind_neu(p, a.neu, neu_slot);
-      bind_dir(p, a.dir, dir_slot);
-      CUresult r_ = g_drv.launchKernel(p->stage[k], p->sgrid.x, p->sgrid.y,
-                                       p->sgrid.z, p->block.x, p->block.y,
-                                       p->block.z, 0, s, params, nullptr);
-      if (r_ != CUDA_SUCCESS) return fail("stage launch: " + cu_err(r_));
-      p->launches += 1;
-      return 0;
-    };
-    auto fused = [&](int k, const double* u, double* u_out, double t_a,
-                     long long neu_a, long long dir_a, double t_b,
-                     long long neu_b, long long dir_b) {
-      PmlFusedArgs f;
-      std::memset(&f, 0, sizeof(f));
-      const unsigned ftx = (unsigned)p->desc.fused_tile[0];
-      const unsigned fty = (unsigned)p->desc.fused_tile[1];
-      const unsigned hy = p->desc.n_dims == 3 ? 1u : 0u;
-      // stage A's stencil input (tile + halo 2); for stages 3+4 also the
-      // step-start state (rows of the stage-A tile) and the accumulator
-      if (state_tensor_map(p, u, ftx + 4, fty + 4 * hy, &f.tm_in)) return -1;
-      if (k == 1) {
-        if (state_tensor_map(p, y, ftx + 4, fty + 2 * hy, &f.tm_y)) return -1;
-        if (state_tensor_map(p, ws->acc, ftx, fty, &f.tm_acc)) return -1;
-      }
-      a.u = u;
-      a.u_out = u_out;
-      a.acc_in = ws->acc;
-      a.acc_out = ws->acc;
-      a.t_eval = t_a;
-      bind_neu(p, a.neu, neu_a);
-      bind_dir(p, a.dir, dir_a);
-      f.s = a;
-      f.t_eval_b = t_b;
-      bind_neu(p, f.neu_b, neu_b);
-      bind_dir(p, f.dir_b, dir_b);
-      void* fparams[] = {&f};
-      CUresult r_ = g_drv.launchKernel(p->fused[k], p->fgrid.x, p->fgrid.y,
-                                       p->fgrid.z, p->fblock.x, p->fblock.y, 1,
-                                       p->fsmem[k], s, fparams, nullptr);
-      if (r_ != CUDA_SUCCESS) return fail("fused launch: " + cu_err(r_));
-      p->launches += 1;
-      return 0;
-    };
-    int rc = 0;
-    // the fused kernels move rows with the TMA unit: 16-byte aligned planes
-    auto aligned = [](const void* q) { return ((uintptr_t)q & 15u) == 0; };
-    const bool use_fused = p->desc.fused && aligned(y) && aligned(y_next) &&
-                           aligned(ws->u_b) && aligned(ws->acc);
-    if (integrator == PML_INTEGRATOR_FORWARD_EULER) {
-      rc = stage(0, y, nullptr, t, s_t, s_f);
-    } else if (use_fused && integrator == PML_INTEGRATOR_EXPLICIT_MIDPOINT) {
-      rc = fused(2, y, nullptr, t, s_t, s_h, t + half, s_h, s_f);
-    } else if (use_fused) {
-      // RK4: stages 1+2 write u_b (= u3) and acc; stages 3+4 write the slot
-      rc = fused(0, y, ws->u_b, t, s_t, s_h, t + half, s_h, s_h);
-      if (!rc) rc = fused(1, ws->u_b, nullptr, t + half, s_h, s_f, t + d_t, s_f, s_f);
-    } else if (integrator == PML_INTEGRATOR_EXPLICIT_MIDPOINT) {
-      rc = stage(1, y, ws->u_a, t, s_t, s_h);
-      if (!rc) rc = stage(2, ws->u_a, nullptr, t + half, s_h, s_f);
-    } else {
-      rc = stage(3, y, ws->u_a, t, s_t, s_h);
-      if (!rc) rc = stage(4, ws->u_a, ws->u_b, t + half, s_h, s_h);
-      if (!rc) rc = stage(5, ws->u_b, ws->u_a, t + half, s_h, s_f);
-      if (!rc) rc = stage(6, ws->u_a, nullptr, t + d_t, s_f, s_f);
-    }
-    if (rc) return rc;
+    const long long s_t = slot0 + 3LL * j, s_f = s_t + 2;
+    if (run_step(p, integrator, ws, a, y, y_next, t, d_t, s_t, -1, nullptr, s))
+      return -1;
     if (p->desc.n_lap > 0) {
       PmlArgs tbl = a;
       bind_neu(p, tbl.neu, s_f);
@@ -632,6 +658,32 @@ int pml_fdm_run(pml_plan* p, int integrator, const pml_workspace* ws,
     }
   }
   return 0;
+}
+
+int pml_fdm_phase_count(const pml_plan* p, int integrator) {
+  if (!p) return fail("null argument");
+  if (integrator == PML_INTEGRATOR_FORWARD_EULER) return 1;
+  if (integrator == PML_INTEGRATOR_EXPLICIT_MIDPOINT) return p->desc.fused ? 1 : 2;
+  if (integrator == PML_INTEGRATOR_RK4) return p->desc.fused ? 2 : 4;
+  return fail("unknown integrator");
+}
+
+int pml_fdm_phase(pml_plan* p, int integrator, const pml_workspace* ws,
+                  const double* y, double* y_next, double t, double d_t,
+                  long long slot0, int phase, double** fresh_out, void* stream) {
+  if (!p || !ws || !y || !y_next) return fail("null argument");
+  if (integrator < 0 || integrator > 2) return fail("unknown integrator");
+  if (p->desc.n_lap > 0 || p->desc.n_alg > 0)
+    return fail("phase-wise stepping needs a fully time-stepped system");
+  if (phase < 0 || phase >= pml_fdm_phase_count(p, integrator))
+    return fail("phase out of range");
+  PmlArgs a;
+  std::memset(&a, 0, sizeof(a));
+  fill_tables(p, a);
+  a.dt = d_t;
+  a.lap_rhs = ws->lap_rhs;
+  return run_step(p, integrator, ws, a, y, y_next, t, d_t, slot0, phase,
+                  fresh_out, (CUstream)stream);
 }
 
 int pml_eval_rhs(pml_plan* p, const double* u, double* out, double t,

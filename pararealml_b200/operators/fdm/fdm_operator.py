@@ -111,6 +111,18 @@ class FDMOperator(Operator):
         #: in HBM and copy it to the host only when the returned ``Solution``
         #: is read; its component planes are ``solution.device_trajectory``
         self.device_resident_solution = False
+        #: extension: cut the mesh into slabs of
+        #: axis 0, one per rank of ``spatial_group`` (default: all ranks of the
+        #: initialised ``torch.distributed`` group), halo planes exchanged
+        #: after every kernel launch; every rank returns the whole ``Solution``
+        #: (gathered lazily, on first read, when ``gather_slabs`` is False)
+        self.spatial_decomposition = False
+        self.spatial_group = None
+        self.gather_slabs = True
+        #: slab solver and local trajectory (component planes of this rank's
+        #: slab incl. halo planes) of the most recent decomposed solve
+        self.last_slab_solver = None
+        self.last_slab_trajectory = None
 
     # ------------------------------------------------------------------
     # plan selection
@@ -243,7 +255,32 @@ class FDMOperator(Operator):
         sol.device_trajectory = traj
         return sol
 
+    def _solve_decomposed(self, ivp) -> Solution:
+        from pararealml_b200.operators.fdm.slab import SlabSolver
+
+        cp = ivp.constrained_problem
+        t = discretize_time_domain(ivp.t_interval, self._d_t)
+        solver = SlabSolver(lowered(cp), self._family, self.spatial_group)
+        y0 = ivp.initial_condition.discrete_y_0(True)
+        y_dev = solver.local_planes(y0)
+        traj = torch.empty(
+            (len(t) - 1, solver.state), dtype=torch.float64, device=y_dev.device
+        )
+        solver.integrate(y_dev, t, self._d_t, traj)
+        self.last_slab_solver = solver
+        self.last_slab_trajectory = traj
+
+        def gather() -> np.ndarray:
+            return solver.gather(traj)
+
+        y = gather() if self.gather_slabs else gather
+        return Solution(
+            ivp, t[1:], y, vertex_oriented=True, d_t=self._d_t, copy=False
+        )
+
     def solve(self, ivp, parallel_enabled: bool = True) -> Solution:
+        if self.spatial_decomposition:
+            return self._solve_decomposed(ivp)
         if self.device_resident_solution:
             return self._solve_lazily(ivp)
         cp, t, y0, low, plan = self.prepare(ivp)

@@ -1,0 +1,237 @@
+"""Spatial slab decomposition of one FDM solve across GPUs (extension; the
+reference has no spatial decomposition).
+
+The mesh is cut along axis 0 into one slab of planes per rank.  A rank
+stores its slab plus ``HALO`` planes of each neighbour and runs the ordinary
+generated kernels on that *local sub-mesh*: they treat its outermost planes as
+mesh faces, which spoils one plane per fused stage from each end -- exactly
+the halo planes, which are overwritten by the neighbours' values after every
+launch (``pml_fdm_phase``).  The planes a rank owns therefore hold the same
+values as in the undecomposed solve.  True mesh faces (first / last rank) keep
+their boundary tables; tables of the other axes and the axis-0 coordinate
+vectors are sliced to the slab.
+
+One rank per GPU with ``torch.distributed``: NCCL moves the halo planes GPU to
+GPU over NVLink; a gloo group (tests, several ranks on one GPU) stages them
+through the host.
+"""
+import ctypes
+from dataclasses import replace
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from pararealml_b200 import _native
+from pararealml_b200.operators.fdm import codegen
+from pararealml_b200.operators.fdm import device as dv
+from pararealml_b200.operators.fdm.lowering import LoweredProblem
+
+#: halo planes per side: a fused stage pair spoils two planes from a local face
+HALO = 2
+
+
+def slab_bounds(n_planes: int, size: int, rank: int) -> Tuple[int, int]:
+    """Planes [z0, z1) of axis 0 owned by ``rank`` (balanced split)."""
+    base, extra = divmod(n_planes, size)
+    z0 = rank * base + min(rank, extra)
+    return z0, z0 + base + (1 if rank < extra else 0)
+
+
+def slab_lowered(low: LoweredProblem, lo: int, hi: int) -> LoweredProblem:
+    """The lowered problem of the sub-mesh of planes [lo, hi) of axis 0."""
+    n0 = low.shape[0]
+    assert 0 <= lo < hi <= n0
+    shape = (hi - lo,) + tuple(low.shape[1:])
+    sub = replace(
+        low,
+        shape=shape,
+        face_static=dict(low.face_static),
+        face_cells={},
+        static_neu={},
+        static_dir={},
+        coords=[c[lo:hi] if a == 0 else c for a, c in enumerate(low.coords)],
+        aux=[
+            (x[lo:hi] if (i == 0 and x is not None) else x)
+            for i, x in enumerate(low.aux)
+        ],
+    )
+    # a face of axis 0 exists only where the slab touches the mesh face
+    drop = (0 if lo == 0 else 1) | (0 if hi == n0 else 2)
+    sub.neu_mask = low.neu_mask & ~drop
+    sub.dir_mask = low.dir_mask & ~drop
+    cells = int(np.prod(shape))
+    for f in range(2 * len(shape)):
+        axis = f // 2
+        sub.face_cells[f] = cells // shape[axis]
+        for src, dst, mask in (
+            (low.static_neu, sub.static_neu, sub.neu_mask),
+            (low.static_dir, sub.static_dir, sub.dir_mask),
+        ):
+            if f not in src or not (mask >> f) & 1:
+                continue
+            if axis == 0:
+                dst[f] = src[f]
+            else:
+                # face cells are ordered (axis 0 index, other index): rows
+                # [lo, hi) of the table
+                row = low.face_cells[f] // n0 * low.y_dim
+                dst[f] = np.ascontiguousarray(src[f][lo * row : hi * row])
+    if hasattr(sub, "_device_static"):
+        del sub._device_static
+    return sub
+
+
+class SlabSolver:
+    """Per-rank state of a slab-decomposed solve of a (static boundary
+    condition, fully time-stepped) problem."""
+
+    def __init__(self, low: LoweredProblem, family: str, group=None):
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("slab decomposition needs torch.distributed")
+        if low.n_dims < 2:
+            raise ValueError("slab decomposition needs a mesh with >= 2 axes")
+        if not low.all_static:
+            raise NotImplementedError(
+                "slab decomposition with dynamic boundary conditions"
+            )
+        if len(low.kind_indices("D_Y_OVER_D_T")) != low.y_dim:
+            raise NotImplementedError(
+                "slab decomposition of systems with algebraic or Poisson equations"
+            )
+        self.group = group
+        self.size = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.on_nccl = dist.get_backend(group) == "nccl"
+        self.low = low
+        self.family = family
+        n0 = low.shape[0]
+        self.z0, self.z1 = slab_bounds(n0, self.size, self.rank)
+        if self.z1 - self.z0 < HALO:
+            raise ValueError(
+                f"{n0} planes over {self.size} ranks leave fewer than {HALO} "
+                "planes per rank"
+            )
+        self.lo = max(self.z0 - HALO, 0)
+        self.hi = min(self.z1 + HALO, n0)
+        self.local = slab_lowered(low, self.lo, self.hi)
+        self.plane = int(np.prod(low.shape[1:]))
+        self.n_loc = self.hi - self.lo
+        self.state = low.y_dim * self.n_loc * self.plane
+        overrides = {
+            "passthrough": False,
+            "fused": codegen.default_fused(self.local.shape, low.y_dim, low.y_dim, False),
+            "small_threads": 0,  # phases are separate launches
+            "zrep": codegen.default_zrep(self.local.shape),
+        }
+        self.plan = dv.get_plan(self.local, **overrides)
+        self.plan.bind_tables(self.local)
+        code = _native.INTEGRATOR_CODES[family]
+        self.code = code
+        self.n_phases = int(_native.lib().pml_fdm_phase_count(self.plan.handle, code))
+        if self.n_phases <= 0:
+            _native.check(-1)
+        ws = self.plan.workspace()
+        self._ws_by_ptr = {
+            t.data_ptr(): t for t in self.plan._ws_bufs.values() if t.numel() >= self.state
+        }
+        self._ws = ws
+        f64 = dict(dtype=torch.float64, device=self.plan.device)
+        n_send = low.y_dim * HALO * self.plane
+        self._pack = [torch.empty(n_send, **f64) for _ in range(2)]
+        self._unpack = [torch.empty(n_send, **f64) for _ in range(2)]
+
+    # -- layout ---------------------------------------------------------------
+    def local_planes(self, y: np.ndarray) -> torch.Tensor:
+        """Channels-last host state of the whole mesh -> component planes of
+        this rank's slab (with halo) on the device."""
+        part = np.ascontiguousarray(y[self.lo : self.hi])
+        return dv.upload_state(part, self.n_loc * self.plane, self.low.y_dim)
+
+    def owned(self, planes: torch.Tensor) -> torch.Tensor:
+        """(..., y_dim * n_loc * plane) -> view (..., y_dim, owned planes, plane)"""
+        lead = planes.shape[:-1]
+        v = planes.view(*lead, self.low.y_dim, self.n_loc, self.plane)
+        return v[..., self.z0 - self.lo : self.z1 - self.lo, :]
+
+    # -- halo exchange ----------------------------------------------------------
+    def exchange(self, buf: torch.Tensor):
+        """Overwrites the halo planes of ``buf`` (y_dim * n_loc * plane
+        doubles) with the neighbours' outermost owned planes."""
+        v = buf.view(self.low.y_dim, self.n_loc, self.plane)
+        a = self.z0 - self.lo  # first owned local plane
+        b = self.z1 - self.lo  # one past the last owned local plane
+        ops, unpacks = [], []
+        shape = (self.low.y_dim, HALO, self.plane)
+        for side, (peer, send_view, halo_view) in enumerate((
+            (self.rank - 1, v[:, a : a + HALO], v[:, a - HALO : a] if a else None),
+            (self.rank + 1, v[:, b - HALO : b], v[:, b : b + HALO] if b < self.n_loc else None),
+        )):
+            if peer < 0 or peer >= self.size:
+                continue
+            self._pack[side].view(shape).copy_(send_view)
+            send, recv = self._pack[side], self._unpack[side]
+            if not self.on_nccl:
+                send, recv = send.cpu(), torch.empty(recv.shape, dtype=recv.dtype)
+            gpeer = peer if self.group is None else dist.get_global_rank(self.group, peer)
+            ops.append(dist.P2POp(dist.isend, send, gpeer, self.group))
+            ops.append(dist.P2POp(dist.irecv, recv, gpeer, self.group))
+            unpacks.append((halo_view, recv, shape))
+        if not ops:
+            return
+        for work in dist.batch_isend_irecv(ops):
+            work.wait()
+        for halo_view, recv, shape in unpacks:
+            halo_view.copy_(recv.view(shape).to(buf.device, non_blocking=True))
+
+    # -- time stepping ----------------------------------------------------------
+    def integrate(self, y0_planes: torch.Tensor, t: np.ndarray, d_t: float,
+                  traj: torch.Tensor):
+        """Steps starting at ``t[:-1]`` from the local planes ``y0_planes``
+        (halo planes valid) into ``traj[j]`` (local planes, halo planes valid
+        on return)."""
+        lib = _native.lib()
+        n_steps = len(t) - 1
+        assert traj.shape == (n_steps, self.state) and traj.is_contiguous()
+        fresh = ctypes.c_void_p()
+        y = y0_planes
+        for j in range(n_steps):
+            y_next = traj[j]
+            for phase in range(self.n_phases):
+                _native.check(
+                    lib.pml_fdm_phase(
+                        self.plan.handle, self.code, ctypes.byref(self._ws),
+                        y.data_ptr(), y_next.data_ptr(), float(t[j]), float(d_t),
+                        0, phase, ctypes.byref(fresh), dv.stream_ptr(),
+                    )
+                )
+                buf = y_next if fresh.value == y_next.data_ptr() else self._ws_by_ptr[fresh.value]
+                self.exchange(buf[: self.state])
+            y = y_next
+
+    # -- gathering ----------------------------------------------------------------
+    def gather(self, traj: torch.Tensor) -> np.ndarray:
+        """The trajectory of the whole mesh, channels-last, on the host of
+        every rank (all-gather of the owned planes)."""
+        n_steps = traj.shape[0]
+        c, n0 = self.low.y_dim, self.low.shape[0]
+        mine = self.owned(traj).contiguous()  # (steps, C, owned, plane)
+        counts = [
+            slab_bounds(n0, self.size, r)[1] - slab_bounds(n0, self.size, r)[0]
+            for r in range(self.size)
+        ]
+        widest = max(counts)
+        padded = torch.zeros((n_steps, c, widest, self.plane), dtype=torch.float64,
+                             device=mine.device if self.on_nccl else "cpu")
+        padded[:, :, : mine.shape[2]] = mine if self.on_nccl else mine.cpu()
+        out = torch.empty((self.size,) + tuple(padded.shape), dtype=torch.float64,
+                          device=padded.device)
+        dist.all_gather_into_tensor(out.view(-1), padded.view(-1), group=self.group)
+        out = out.cpu().numpy()
+        full = np.empty((n_steps, n0, self.plane, c))
+        for r in range(self.size):
+            z0, z1 = slab_bounds(n0, self.size, r)
+            # (steps, C, planes, plane) -> (steps, planes, plane, C)
+            full[:, z0:z1] = np.moveaxis(out[r][:, :, : z1 - z0], 1, -1)
+        return full.reshape((n_steps,) + tuple(self.low.shape) + (c,))

@@ -68,6 +68,38 @@ def convection_diffusion_3d_mixed(shape):
     return cp, y0, 1e-5
 
 
+def convection_diffusion_3d_static(shape):
+    """Dirichlet, Neumann faces on every axis, all static."""
+    eq = ns.ConvectionDiffusionEquation(3, [0.3, -0.2, 0.1], 0.05)
+    mesh = ns.Mesh([(0.0, 1.0)] * 3, [1.0 / (n - 1) for n in shape])
+    bcs = [
+        (
+            ns.DirichletBoundaryCondition(
+                lambda x, t: np.full((len(x), 1), 0.5), is_static=True
+            ),
+            ns.NeumannBoundaryCondition(_zeros(1), is_static=True),
+        ),
+        (
+            ns.NeumannBoundaryCondition(
+                lambda x, t: x[:, :1] * 0.25, is_static=True
+            ),
+            ns.DirichletBoundaryCondition(
+                lambda x, t: x[:, :1] + x[:, 2:3], is_static=True
+            ),
+        ),
+        (
+            ns.DirichletBoundaryCondition(
+                lambda x, t: 1.0 + x[:, :1] * x[:, 1:2], is_static=True
+            ),
+            ns.NeumannBoundaryCondition(_zeros(1), is_static=True),
+        ),
+    ]
+    cp = ns.ConstrainedProblem(eq, mesh, bcs)
+    rng = np.random.default_rng(5)
+    y0 = rng.uniform(0.0, 1.0, mesh.vertices_shape + (1,))
+    return cp, y0, 1e-5
+
+
 def cahn_hilliard_3d(shape):
     """An algebraic (LHS.Y) component next to the time-stepped one."""
     eq = ns.CahnHilliardEquation(3, gamma=0.5)

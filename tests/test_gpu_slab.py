@@ -1,0 +1,96 @@
+"""Spatial slab decomposition (extension): several
+ranks, each owning a slab of axis 0 plus two halo planes per neighbour, must
+reproduce the undecomposed solve.  Ranks share cuda:0 through a gloo group
+here (halo planes staged through the host); one rank per GPU over NCCL where
+two GPUs exist."""
+import numpy as np
+import pytest
+
+from dist_util import run_distributed
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(name):
+    import pararealml_b200 as ns
+    import test_gpu_fused as tf
+
+    builder, shape = {
+        "burgers_3d": (tf.burgers_3d, (26, 21, 22)),
+        "convection_diffusion_3d_mixed": (tf.convection_diffusion_3d_static, (23, 19, 38)),
+        "diffusion_2d": (tf.diffusion_2d, (45, 50)),
+        "shallow_water_polar": (tf.shallow_water_polar, (70, 300)),
+    }[name]
+    cp, y0, d_t = builder(shape)
+    ivp = ns.InitialValueProblem(
+        cp, (0.0, 3 * d_t), ns.DiscreteInitialCondition(cp, y0, True)
+    )
+    return ns, ivp, d_t
+
+
+def _operator(integrator, d_t):
+    from pararealml_b200.operators.fdm import (
+        RK4, ExplicitMidpointMethod, FDMOperator, ForwardEulerMethod,
+        ThreePointCentralDifferenceMethod,
+    )
+
+    kinds = {"rk4": RK4, "midpoint": ExplicitMidpointMethod, "euler": ForwardEulerMethod}
+    return FDMOperator(kinds[integrator](), ThreePointCentralDifferenceMethod(), d_t)
+
+
+def _worker(rank, world_size, name, integrator, fuse):
+    import os
+
+    import torch
+
+    os.environ["PML_SMALL"] = "0"
+    os.environ["PML_FUSE"] = fuse
+    if torch.cuda.device_count() >= world_size and os.environ.get("PML_TEST_NCCL") == "1":
+        torch.cuda.set_device(rank)
+    else:
+        torch.cuda.set_device(0)
+    from common import per_step_rel_err
+
+    ns, ivp, d_t = _problem(name)
+    whole = _operator(integrator, d_t).solve(ivp).discrete_y()
+    op = _operator(integrator, d_t)
+    op.spatial_decomposition = True
+    sol = op.solve(ivp)
+    y = sol.discrete_y()
+    assert y.shape == whole.shape
+    assert np.isfinite(y).all()
+    solver = op.last_slab_solver
+    assert solver.size == world_size and solver.z1 - solver.z0 >= 2
+    # same kernels, same operation order per cell (the warp-level choice of the
+    # boundary-free instantiation may differ: FMA contraction, <= 1 ulp)
+    assert per_step_rel_err(y, whole) <= 1e-14
+    lazy = _operator(integrator, d_t)
+    lazy.spatial_decomposition = True
+    lazy.gather_slabs = False
+    assert np.array_equal(lazy.solve(ivp).discrete_y(), y)
+
+
+@pytest.mark.parametrize("world_size", [2, 3])
+@pytest.mark.parametrize(
+    "name,integrator,fuse",
+    [
+        ("burgers_3d", "rk4", "1"),
+        ("burgers_3d", "rk4", "0"),
+        ("burgers_3d", "midpoint", "1"),
+        ("convection_diffusion_3d_mixed", "rk4", "1"),
+        ("diffusion_2d", "rk4", "1"),
+        ("diffusion_2d", "euler", "1"),
+        ("shallow_water_polar", "rk4", "1"),
+    ],
+)
+def test_slabs_reproduce_the_undecomposed_solve(name, integrator, fuse, world_size):
+    run_distributed(_worker, world_size, (name, integrator, fuse))
+
+
+def test_slabs_over_nccl_one_rank_per_gpu(monkeypatch):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    monkeypatch.setenv("PML_TEST_NCCL", "1")
+    run_distributed(_worker, 2, ("burgers_3d", "rk4", "1"), backend="nccl")
