@@ -141,6 +141,7 @@ class SlabSolver:
         n_send = low.y_dim * HALO * self.plane
         self._pack = [torch.empty(n_send, **f64) for _ in range(2)]
         self._unpack = [torch.empty(n_send, **f64) for _ in range(2)]
+        self._ops = None  # NCCL: the four transfers, built once
 
     # -- layout ---------------------------------------------------------------
     def local_planes(self, y: np.ndarray) -> torch.Tensor:
@@ -156,34 +157,56 @@ class SlabSolver:
         return v[..., self.z0 - self.lo : self.z1 - self.lo, :]
 
     # -- halo exchange ----------------------------------------------------------
+    def _neighbours(self, v: torch.Tensor):
+        """(side, peer, planes to send, halo planes to fill) of ``v``
+        (y_dim, n_loc, plane)."""
+        a = self.z0 - self.lo  # first owned local plane
+        b = self.z1 - self.lo  # one past the last owned local plane
+        out = []
+        if self.rank > 0:
+            out.append((0, self.rank - 1, v[:, a : a + HALO], v[:, a - HALO : a]))
+        if self.rank + 1 < self.size:
+            out.append((1, self.rank + 1, v[:, b - HALO : b], v[:, b : b + HALO]))
+        return out
+
+    def _global(self, peer: int) -> int:
+        return peer if self.group is None else dist.get_global_rank(self.group, peer)
+
     def exchange(self, buf: torch.Tensor):
         """Overwrites the halo planes of ``buf`` (y_dim * n_loc * plane
         doubles) with the neighbours' outermost owned planes."""
         v = buf.view(self.low.y_dim, self.n_loc, self.plane)
-        a = self.z0 - self.lo  # first owned local plane
-        b = self.z1 - self.lo  # one past the last owned local plane
-        ops, unpacks = [], []
         shape = (self.low.y_dim, HALO, self.plane)
-        for side, (peer, send_view, halo_view) in enumerate((
-            (self.rank - 1, v[:, a : a + HALO], v[:, a - HALO : a] if a else None),
-            (self.rank + 1, v[:, b - HALO : b], v[:, b : b + HALO] if b < self.n_loc else None),
-        )):
-            if peer < 0 or peer >= self.size:
-                continue
-            self._pack[side].view(shape).copy_(send_view)
-            send, recv = self._pack[side], self._unpack[side]
-            if not self.on_nccl:
-                send, recv = send.cpu(), torch.empty(recv.shape, dtype=recv.dtype)
-            gpeer = peer if self.group is None else dist.get_global_rank(self.group, peer)
-            ops.append(dist.P2POp(dist.isend, send, gpeer, self.group))
-            ops.append(dist.P2POp(dist.irecv, recv, gpeer, self.group))
-            unpacks.append((halo_view, recv, shape))
-        if not ops:
+        sides = self._neighbours(v)
+        if not sides:
             return
+        for side, _, send_view, _ in sides:
+            self._pack[side].view(shape).copy_(send_view)
+        if self.on_nccl:
+            # GPU to GPU over NVLink, one grouped launch for all four transfers
+            if self._ops is None:
+                self._ops = []
+                for side, peer, _, _ in sides:
+                    g = self._global(peer)
+                    self._ops.append(dist.P2POp(dist.isend, self._pack[side], g, self.group))
+                    self._ops.append(dist.P2POp(dist.irecv, self._unpack[side], g, self.group))
+            for work in dist.batch_isend_irecv(self._ops):
+                work.wait()
+            for side, _, _, halo_view in sides:
+                halo_view.copy_(self._unpack[side].view(shape))
+            return
+        # gloo (tests, ranks sharing a GPU): staged through the host
+        ops, staged = [], []
+        for side, peer, _, halo_view in sides:
+            g = self._global(peer)
+            recv = torch.empty(self._unpack[side].shape, dtype=torch.float64)
+            ops.append(dist.P2POp(dist.isend, self._pack[side].cpu(), g, self.group))
+            ops.append(dist.P2POp(dist.irecv, recv, g, self.group))
+            staged.append((halo_view, recv))
         for work in dist.batch_isend_irecv(ops):
             work.wait()
-        for halo_view, recv, shape in unpacks:
-            halo_view.copy_(recv.view(shape).to(buf.device, non_blocking=True))
+        for halo_view, recv in staged:
+            halo_view.copy_(recv.view(shape).to(buf.device))
 
     # -- time stepping ----------------------------------------------------------
     def integrate(self, y0_planes: torch.Tensor, t: np.ndarray, d_t: float,
