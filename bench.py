@@ -830,6 +830,8 @@ def run_b200(args):
 
 def main():
     args = parse_args()
+    # the timed region continues from the last warm-up step: at least one
+    args.warmup = max(args.warmup, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
