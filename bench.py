@@ -585,11 +585,16 @@ def run_b200(args):
             # the same solve with the trajectory left in HBM (lazy Solution):
             # only the final state is read back
             op_e.device_resident_solution = True
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            sol = op_e.solve(ivp_e)
-            last = sol.device_trajectory[-1].cpu()
-            dt_l = time.perf_counter() - t0
+            last = torch.empty(y_dim * cells, dtype=torch.float64, pin_memory=True)
+            dt_l = None
+            for _ in range(2):  # the first pass primes the allocators
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                sol = op_e.solve(ivp_e)
+                last.copy_(sol.device_trajectory[-1], non_blocking=True)
+                torch.cuda.synchronize()
+                dt_l = time.perf_counter() - t0
+                del sol
             e2e["device_resident"] = {
                 "value": cells * args.e2e_steps / dt_l / 1e9,
                 "unit": UNIT,
@@ -599,7 +604,7 @@ def run_b200(args):
                         "trajectory stays in HBM behind a lazy Solution, only "
                         "the final state is copied to the host",
             }
-            del sol, last
+            del last
         cpu = None
         if not args.no_cpu_baseline and args.workload != "navier_stokes_2d":
             # (the oracle's Jacobi solve iterates to tolerance: no bounded
