@@ -543,11 +543,13 @@ PML_STAGE_KERNEL(pml_stage_rk4_4, PML_RK4_4)
 //
 // A thread block owns a PML_FTX x PML_FTY tile of the in-plane axes and marches
 // along axis 0 over PML_FZC planes.  Per plane ("iteration" i):
-//   * the TMA unit (cp.async.bulk, one row per copy, completion on an mbarrier)
-//     streams the stencil input of stage A (tile + 2 halo cells) into a ring of
-//     shared-memory planes, PML_FDEPTH iterations ahead; for stages 3+4 also
-//     the step-start state and the RK4 accumulator.  No thread ever waits on a
-//     global load, and no registers are tied up by prefetches;
+//   * the TMA unit (cp.async.bulk.tensor, one box per component plane, issued
+//     by one elected lane each, completion counted on an mbarrier) streams the
+//     stencil input of stage A (tile + 2 halo cells; cells outside the mesh
+//     arrive as zeros) into a ring of shared-memory planes, PML_FDEPTH
+//     iterations ahead; for stages 3+4 also the step-start state and the RK4
+//     accumulator.  No thread ever waits on a global load, and no registers
+//     are tied up by prefetches;
 //   * stage A is evaluated on plane i + 1 for the tile plus ONE halo cell (one
 //     thread per cell) with every stencil operand read from the input ring;
 //     its result goes to a 4-slot ring of shared-memory planes;
