@@ -5,7 +5,7 @@ streams here.
 import ctypes
 import os
 import warnings
-from typing import Dict, Optional, Sequence
+from typing import Dict, Optional
 
 import numpy as np
 import torch

@@ -17,7 +17,7 @@ through the host.
 """
 import ctypes
 from dataclasses import replace
-from typing import List, Optional, Tuple
+from typing import Tuple
 
 import numpy as np
 import torch

@@ -28,9 +28,8 @@ all states stay on the device (component planes) and the updates run as CUDA
 kernels through the C ABI (``pml_parareal_*``); any other ``Operator`` pair
 goes through the generic path that exchanges host arrays.
 """
-import ctypes
 import sys
-from typing import Callable, Optional, Sequence, Union
+from typing import Callable, Sequence, Union
 
 import numpy as np
 import torch
