@@ -37,6 +37,13 @@ def metric_name(workload, n):
     return f"fp64 FDM cell-steps/s ({workload} {n}, RK4)"
 
 
+def parareal_metric(workload, n):
+    """N > 1: a Parareal solve, one time slice per GPU -- its own metric name
+    (the value still counts cell-steps of the fine trajectory per second)."""
+    return (f"fp64 Parareal cell-steps/s ({workload} {n}, fine RK4 / coarse "
+            "ForwardEuler, one time slice per GPU)")
+
+
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
@@ -54,7 +61,9 @@ def parse_args():
     p.add_argument("--parareal-tol", type=float, default=1e-6,
                    help="RMS end point update tolerance (states are O(1))")
     p.add_argument("--cpu-grid", type=int, default=96)
-    p.add_argument("--cpu-parareal-grid", type=int, default=32,
+    p.add_argument("--reference-timeout", type=float, default=240.0,
+                   help="wall-clock bound (s) of the reference arm's host work")
+    p.add_argument("--cpu-parareal-grid", type=int, default=40,
                    help="vertices per axis of the host-process Parareal sample")
     p.add_argument("--jacobi-sweeps", type=int, default=100,
                    help="cap on Jacobi sweeps per step (navier_stokes_2d; the "
@@ -325,82 +334,179 @@ def load_traffic():
 # ---------------------------------------------------------------------------
 # reference arm
 # ---------------------------------------------------------------------------
+#: launcher variables a spawned host worker must not inherit: under
+#: ``torch.distributed.run`` TORCHELASTIC_USE_AGENT_STORE makes every
+#: ``init_process_group`` a TCPStore *client* of the agent's store
+_LAUNCHER_ENV = (
+    "RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK",
+    "ROLE_RANK", "ROLE_WORLD_SIZE", "GROUP_WORLD_SIZE", "MASTER_ADDR",
+    "MASTER_PORT", "ROLE_NAME", "OMP_NUM_THREADS",
+)
+
+
+def reference_namespace():
+    """``(ns, fdm_ops, parareal_cls, kind)``: the UNMODIFIED reference from
+    ``baseline/_ref`` (offline pip install made by ``build()``; or
+    ``PML_REFERENCE_ROOT``) behind the import shim of ``tests/refshim.py``
+    when present -- ``kind`` "reference" -- else ``None`` and the caller falls
+    back to the oracle port.  ``/root/reference`` is never read here."""
+    if os.environ.get("PML_BENCH_PORT_ONLY") == "1":
+        return None
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    try:
+        import refshim
+    except ImportError:
+        return None
+    root = refshim.REFERENCE_ROOT
+    if os.path.abspath(root).startswith("/root/reference") or not refshim.available():
+        return None
+    try:
+        ref = refshim.install()
+        from pararealml.operators import fdm as ref_fdm
+        from pararealml.operators.parareal import PararealOperator as RefParareal
+    except Exception:  # an unusable install must not take the arm down
+        return None
+    return ref, ref_fdm, RefParareal, refshim
+
+
 def _reference_parareal_worker(rank, world, port, n, slice_steps, ratio, tol,
                                steps, warmup, out):
     """One host process = one time slice of the reference's mpirun layout."""
+    for k in list(os.environ):
+        if k in _LAUNCHER_ENV or k.startswith("TORCHELASTIC_"):
+            del os.environ[k]
+    import torch
     import torch.distributed as dist
 
-    import oracle
-    import pararealml_b200 as ns
-    from oracle.parareal_ranks import GlooComm, parareal_rank_solve
+    torch.set_num_threads(1)
+    store = dist.TCPStore("127.0.0.1", port, world, is_master=(rank == 0))
+    dist.init_process_group("gloo", store=store, rank=rank, world_size=world)
 
-    dist.init_process_group(
-        "gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world
-    )
-    ivp, d_t = burgers_problem(ns, n, world * slice_steps)
-    f = oracle.OracleFDMOperator("rk4", d_t)
-    g = oracle.OracleFDMOperator("forward_euler", d_t * ratio)
-    comm = GlooComm()
+    found = reference_namespace()
+    if found is not None:
+        ref, ref_fdm, RefParareal, refshim = found
+        refshim.set_comm(refshim.GlooComm())
+        ivp, d_t = burgers_problem(ref, n, world * slice_steps)
+        tcd = ref_fdm.ThreePointCentralDifferenceMethod
+        f = ref_fdm.FDMOperator(ref_fdm.RK4(), tcd(), d_t)
+        g = ref_fdm.FDMOperator(ref_fdm.ForwardEulerMethod(), tcd(), d_t * ratio)
+        p = RefParareal(f, g, tol)
+        count = [0]
+        inner = p._should_terminate
 
-    def sub_ivp(cp, interval, y0):
-        return ns.InitialValueProblem(
-            cp, interval, ns.DiscreteInitialCondition(cp, y0, True)
-        )
+        def counting(old, new):
+            count[0] += 1
+            return inner(old, new)
+
+        p._should_terminate = counting
+
+        def solve():
+            count[0] = 0
+            p.solve(ivp)
+            return count[0]
+
+        kind = "reference"
+    else:
+        import oracle
+        import pararealml_b200 as ns
+        from oracle.parareal_ranks import GlooComm, parareal_rank_solve
+
+        ivp, d_t = burgers_problem(ns, n, world * slice_steps)
+        f = oracle.OracleFDMOperator("rk4", d_t)
+        g = oracle.OracleFDMOperator("forward_euler", d_t * ratio)
+        comm = GlooComm()
+
+        def sub_ivp(cp, interval, y0):
+            return ns.InitialValueProblem(
+                cp, interval, ns.DiscreteInitialCondition(cp, y0, True)
+            )
+
+        def solve():
+            return parareal_rank_solve(comm, ivp, f, g, tol, sub_ivp)[2]
+
+        kind = "port"
 
     iterations = 0
     for _ in range(warmup):
-        parareal_rank_solve(comm, ivp, f, g, tol, sub_ivp)
-    comm.barrier()
+        solve()
+    dist.barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
-        _, _, iterations = parareal_rank_solve(comm, ivp, f, g, tol, sub_ivp)
-    comm.barrier()
+        iterations = solve()
+    dist.barrier()
     if rank == 0:
-        out.put((time.perf_counter() - t0, iterations))
+        out.put((time.perf_counter() - t0, iterations, kind))
     dist.destroy_process_group()
 
 
 def run_reference_parareal(args):
-    """N > 1: the reference's Parareal (oracle port, SPMD with Allgathers) on
-    N host processes -- the stand-in for ``mpirun -n N`` (no MPI runtime in
-    the image)."""
+    """N > 1: the reference's Parareal on N host processes, one per time
+    slice, the way ``mpirun -n N`` runs it (Makefile:36-37): the unmodified
+    reference from ``baseline/_ref`` with a gloo group behind the ``mpi4py``
+    shim, else the oracle port (no MPI runtime exists in the image)."""
     import socket
 
     import torch.multiprocessing as mp
 
     world = args.gpus
     n = args.cpu_parareal_grid
+    steps = max(1, min(args.steps, 3))
+    warmup = min(args.warmup, 1)
     with socket.socket() as sock:
         sock.bind(("127.0.0.1", 0))
         port = sock.getsockname()[1]
     ctx = mp.get_context("spawn")
     out = ctx.SimpleQueue()
-    mp.spawn(
+    spawned = mp.spawn(
         _reference_parareal_worker,
         args=(world, port, n, args.slice_steps, args.coarse_ratio,
-              args.parareal_tol, args.steps, args.warmup, out),
-        nprocs=world, join=True,
+              args.parareal_tol, steps, warmup, out),
+        nprocs=world, join=False,
     )
-    dt, iterations = out.get()
+    # watchdog: the arm must print a line even if a worker hangs
+    deadline = time.monotonic() + args.reference_timeout
+    error = None
+    try:
+        while not spawned.join(timeout=1.0):
+            if time.monotonic() > deadline:
+                error = f"host workers exceeded {args.reference_timeout} s"
+                for proc in spawned.processes:
+                    if proc.is_alive():
+                        proc.kill()
+                break
+    except Exception as exc:
+        error = f"{type(exc).__name__}: {str(exc)[:300]}"
+    if error is None and not out.empty():
+        dt, iterations, kind = out.get()
+    else:
+        error = error or "no result from the host workers"
+        dt, iterations, kind = float("nan"), 0, "port"
     total_steps = world * args.slice_steps
-    value = n**3 * total_steps * args.steps / dt / 1e9
+    value = None if error else n**3 * total_steps * steps / dt / 1e9
+    wall_ms = None if error else dt / steps * 1e3
+    impl = (
+        "the unmodified reference PararealOperator (baseline/_ref, gloo "
+        "Allgather behind the mpi4py shim)"
+        if kind == "reference"
+        else "oracle port of the reference PararealOperator (gloo Allgather)"
+    )
     sample = (
-        f"oracle port of the reference PararealOperator (f = NumPy FDM RK4, "
-        f"g = ForwardEuler at {args.coarse_ratio} d_t) on {world} host "
-        f"processes (gloo Allgather standing in for mpirun; "
-        f"{os.cpu_count()} host cores), 3-D Burgers on {n}^3 (bounded sample "
+        f"{impl}: f = NumPy FDM RK4, g = ForwardEuler at {args.coarse_ratio} "
+        f"d_t, {world} host processes standing in for mpirun -n {world} "
+        f"({os.cpu_count()} host cores), 3-D Burgers on {n}^3 (bounded sample "
         f"of the 512^3 workload), {world} slices x {args.slice_steps} fine "
-        f"steps, {iterations} Parareal iterations per solve"
+        f"steps, {iterations} Parareal iterations per solve, {steps} timed "
+        f"solves"
     )
     line = {
         "impl": "reference",
-        "metric": METRIC,
+        "metric": parareal_metric(args.workload, 512),
         "value": value,
         "unit": UNIT,
         "n_gpus": world,
-        "steps": args.steps,
-        "warmup": args.warmup,
-        "ms_per_step": dt / args.steps * 1e3,
+        "steps": steps,
+        "warmup": warmup,
+        "ms_per_step": wall_ms,
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
@@ -412,15 +518,18 @@ def run_reference_parareal(args):
                         f"of the 512^3 workload, {world} time slices x "
                         f"{args.slice_steps} fine steps, tol {args.parareal_tol}",
             "parareal_iterations": iterations,
+            "wall_ms_per_solve": wall_ms,
         },
         "cpu_baseline": {
-            "value": value, "unit": UNIT, "cores": world, "kind": "port",
+            "value": value, "unit": UNIT, "cores": world, "kind": kind,
             "sample": sample,
         },
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if error:
+        line["error"] = error
     print(json.dumps(line), flush=True)
 
 
@@ -431,12 +540,32 @@ def run_reference(args):
     if args.gpus > 1:
         run_reference_parareal(args)
         return
-    import oracle
-    import pararealml_b200 as ns
-
     n = args.cpu_grid
-    ivp, d_t = burgers_problem(ns, n, 1)
-    from oracle.fdm import fdm_solve
+    found = reference_namespace()
+    if found is not None:
+        ref, ref_fdm, _, _ = found
+        ivp, d_t = burgers_problem(ref, n, 1)
+        op = ref_fdm.FDMOperator(
+            ref_fdm.RK4(), ref_fdm.ThreePointCentralDifferenceMethod(), d_t
+        )
+        ns = ref
+
+        def solve(sub):
+            return op.solve(sub).discrete_y()[-1]
+
+        kind = "reference"
+        what = "the unmodified reference FDMOperator (baseline/_ref)"
+    else:
+        import pararealml_b200 as ns
+        from oracle.fdm import fdm_solve
+
+        ivp, d_t = burgers_problem(ns, n, 1)
+
+        def solve(sub):
+            return fdm_solve(sub, "rk4", d_t)[1][-1]
+
+        kind = "port"
+        what = "oracle port of the reference NumPy FDMOperator"
 
     cp = ivp.constrained_problem
     y = ivp.initial_condition.discrete_y_0(True)
@@ -445,20 +574,26 @@ def run_reference(args):
         sub = ns.InitialValueProblem(
             cp, (0.0, d_t), ns.DiscreteInitialCondition(cp, y_in, True)
         )
-        return fdm_solve(sub, "rk4", d_t)[1][-1]
+        return solve(sub)
 
+    # bounded: the whole run must end within a few minutes on any host
+    budget = time.monotonic() + args.reference_timeout
+    steps_done = 0
     for _ in range(args.warmup):
         y = one_step(y)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         y = one_step(y)
+        steps_done += 1
+        if time.monotonic() > budget:
+            break
     dt = time.perf_counter() - t0
-    value = n**3 * args.steps / dt / 1e9
+    value = n**3 * steps_done / dt / 1e9
     sample = (
-        f"oracle port of the reference NumPy FDMOperator (RK4, "
-        f"ThreePointCentralDifferenceMethod), 3-D Burgers on {n}^3 "
-        f"(bounded sample of the 512^3 workload), {args.steps} steps, "
-        "single process (NumPy stencils are single-threaded)"
+        f"{what} (RK4, ThreePointCentralDifferenceMethod), 3-D Burgers on "
+        f"{n}^3 (bounded sample of the 512^3 workload), {steps_done} steps, "
+        f"single process ({os.cpu_count()} host cores present; the "
+        "reference's NumPy stencils are single-threaded)"
     )
     line = {
         "impl": "reference",
@@ -466,9 +601,9 @@ def run_reference(args):
         "value": value,
         "unit": UNIT,
         "n_gpus": args.gpus,
-        "steps": args.steps,
+        "steps": steps_done,
         "warmup": args.warmup,
-        "ms_per_step": dt / args.steps * 1e3,
+        "ms_per_step": dt / steps_done * 1e3,
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
@@ -476,7 +611,7 @@ def run_reference(args):
         "data": "synthetic",
         "config": {"workload": f"3-D Burgers RK4 FDM, {n}^3 sample of the 512^3 workload"},
         "cpu_baseline": {
-            "value": value, "unit": UNIT, "cores": 1, "kind": "port",
+            "value": value, "unit": UNIT, "cores": 1, "kind": kind,
             "sample": sample,
         },
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,

@@ -14,6 +14,8 @@
 #include <cuda_runtime.h>
 #include <nvrtc.h>
 
+#include <unistd.h>
+
 #include <cmath>
 #include <cstdio>
 #include <cstdint>
@@ -188,8 +190,12 @@ bool read_file(const char* path, std::vector<char>& out) {
   return !out.empty();
 }
 
+// atomic publish: every writer stages through its own temporary name (ranks
+// that compile the same kernel at the same time must not share one inode)
 bool write_file(const char* path, const std::vector<char>& data) {
-  std::string tmp = std::string(path) + ".tmp";
+  static unsigned counter = 0;
+  std::string tmp = std::string(path) + ".tmp" + std::to_string((long long)getpid()) +
+                    "." + std::to_string(counter++);
   {
     std::ofstream f(tmp, std::ios::binary);
     if (!f) return false;

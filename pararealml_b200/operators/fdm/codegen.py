@@ -160,6 +160,9 @@ def default_fused(shape, y_dim, n_dt=None, passthrough=False) -> Optional[FusedT
     n_dt = y_dim if n_dt is None else n_dt
     if nd < 2 or any(n < 3 for n in shape) or n_dt < 1 or shape[-1] % 2:
         return None
+    if any(n > 65534 for n in shape[1:]):
+        # the pair kernels pack the in-plane coordinates into 16-bit fields
+        return None
     # by default only systems whose components are all time-stepped: algebraic
     # (LHS.Y) and Poisson components are stencil inputs that never change
     # within a step, which the unfused kernels serve from L2 at no extra cost

@@ -12,7 +12,26 @@ from unittest.mock import MagicMock
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("PML_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_reference_root():
+    """``PML_REFERENCE_ROOT``, else the offline install under
+    ``baseline/_ref`` (made by ``__graft_entry__.build()``; it travels to the
+    GPU box with the snapshot), else the read-only checkout of the build
+    container."""
+    candidates = [
+        os.environ.get("PML_REFERENCE_ROOT"),
+        os.path.join(_REPO, "baseline", "_ref"),
+        "/root/reference",
+    ]
+    for c in candidates:
+        if c and os.path.isdir(os.path.join(c, "pararealml")):
+            return c
+    return candidates[0] or candidates[-1]
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 
 class FakeComm:
@@ -64,7 +83,45 @@ class FakeComm:
         self._barrier.wait()
 
 
+class GlooComm:
+    """Process-per-rank stand-in for ``MPI.COMM_WORLD`` on a
+    ``torch.distributed`` gloo group (timed host baselines: true parallelism,
+    which the thread-per-rank communicator cannot give under the GIL)."""
+
+    def __init__(self):
+        import torch.distributed as dist
+
+        self._dist = dist
+        self.size = dist.get_world_size()
+        self.rank = dist.get_rank()
+
+    def Get_size(self):
+        return self.size
+
+    def Get_rank(self):
+        return self.rank
+
+    def barrier(self):
+        self._dist.barrier()
+
+    Barrier = barrier
+
+    def Allgather(self, send, recv):
+        import torch
+
+        send_buf = send[0] if isinstance(send, (list, tuple)) else send
+        recv_buf = recv[0] if isinstance(recv, (list, tuple)) else recv
+        out = torch.from_numpy(recv_buf).view(-1)
+        src = torch.from_numpy(np.ascontiguousarray(send_buf)).view(-1)
+        self._dist.all_gather_into_tensor(out, src)
+
+
 COMM = FakeComm()
+
+
+def set_comm(comm):
+    """Replaces ``mpi4py.MPI.COMM_WORLD`` of the (already installed) shim."""
+    sys.modules["mpi4py.MPI"].COMM_WORLD = comm
 
 
 def available():
