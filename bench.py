@@ -69,6 +69,12 @@ def parse_args():
                    help="cap on Jacobi sweeps per step (navier_stokes_2d; the "
                         "reference iterates to tolerance, 1e3..1e7 sweeps)")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-workloads", action="store_true",
+                   help="N = 1: skip the other named configurations")
+    p.add_argument("--no-parity", action="store_true",
+                   help="skip the parity checks that precede the timed region")
+    p.add_argument("--parity-grid-3d", type=int, default=256)
+    p.add_argument("--parity-grid-2d", type=int, default=2048)
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-spatial", action="store_true",
                    help="N > 1: skip the slab-decomposed solve")
@@ -622,6 +628,320 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------
+# parity checks at benchmark scale (outside every timed region; the oracle is
+# used here only as the checker)
+# ---------------------------------------------------------------------------
+def _rel(a, b):
+    scale = float(np.max(np.abs(b)))
+    return float(np.max(np.abs(a - b)) / (scale if scale else 1.0))
+
+
+def parity_single_gpu(args, ns, FDMOperator, RK4, TCD, dv, torch):
+    """N = 1: (1) one RK4 step of the 256^3 Burgers problem and of the 2048^2
+    polar shallow-water problem through ``FDMOperator.solve`` against the
+    oracle (<= 1e-12, SURVEY.md section 8d "single step at full size where RAM
+    allows"); (2) one step of the benchmark mesh itself, fused stage-pair
+    kernels against the one-launch-per-stage kernels on the device
+    (<= 1e-14) -- this exercises the chunking, the grid and the > 2^31-byte
+    offsets of the timed run."""
+    import oracle
+    from pararealml_b200.operators.fdm.fdm_operator import plan_overrides
+
+    out = []
+    for workload, n in (("burgers_3d", args.parity_grid_3d),
+                        ("shallow_water_polar", args.parity_grid_2d)):
+        if n <= 0:
+            continue
+        builder = WORKLOADS[workload][0]
+        ivp, d_t = builder(ns, n, 1)
+        op = FDMOperator(RK4(), TCD(), d_t)
+        y = op.solve(ivp).discrete_y()
+        plan = op.prepare(ivp)[-1]
+        t0 = time.perf_counter()
+        _, y_ref = oracle.fdm_solve(ivp, "rk4", d_t)
+        secs = time.perf_counter() - t0
+        err = _rel(y[0], y_ref[0])
+        out.append({
+            "case": f"{workload} {'x'.join([str(n)] * WORKLOADS[workload][3])}, "
+                    "one RK4 step, FDMOperator.solve vs oracle.fdm_solve",
+            "kernels": "fused stage pairs" if plan.fused is not None else "stage kernels",
+            "max_rel_err": err, "tolerance": 1e-12, "ok": bool(err <= 1e-12),
+            "oracle_seconds": round(secs, 1),
+        })
+        del y, y_ref
+    # the benchmark mesh: fused pairs vs stage kernels, on the device
+    builder, n_default = WORKLOADS[args.workload][:2]
+    n = args.grid or n_default
+    ivp, d_t = builder(ns, n, 1)
+    op = FDMOperator(RK4(), TCD(), d_t)
+    if args.workload == "navier_stokes_2d":
+        op.max_jacobi_sweeps = args.jacobi_sweeps
+    cp, t, y0, low, plan = op.prepare(ivp)
+    if plan.fused is not None:
+        ov = plan_overrides(cp, low, y0)
+        ov["fused"] = None
+        plan_u = dv.get_plan(low, **ov)
+        y_dev = dv.upload_state(y0, low.n_cells, low.y_dim)
+        res = []
+        for pl in (plan, plan_u):
+            traj = torch.empty((1, low.y_dim * low.n_cells), dtype=torch.float64,
+                               device="cuda")
+            op.integrate_on_device(cp, pl, y_dev, t, traj)
+            res.append(traj)
+        torch.cuda.synchronize()
+        scale = float(res[1].abs().max().item())
+        err = float((res[0] - res[1]).abs().max().item()) / (scale if scale else 1.0)
+        out.append({
+            "case": f"{args.workload} {'x'.join(str(v) for v in low.shape)}, one "
+                    "RK4 step on the device, fused stage pairs vs stage kernels",
+            "max_rel_err": err, "tolerance": 1e-14, "ok": bool(err <= 1e-14),
+        })
+        del res, traj, y_dev
+        torch.cuda.empty_cache()
+    return out
+
+
+def parity_multi_gpu(world, rank, ns, FDMOperator, RK4, FE, TCD, Parareal, torch):
+    """N > 1, over the live NCCL group: (1) the multi-rank golden trajectories
+    of the unmodified reference (tests/golden, P = world) -- trajectory error
+    and iteration count; (2) a Parareal solve on a mesh that runs the fused
+    stage-pair kernels against the oracle's P-rank emulation; (3) the
+    slab-decomposed solve against the undecomposed one."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle
+    from common import load_golden, per_step_rel_err
+    from golden import cases
+
+    kinds = {"rk4": RK4, "forward_euler": FE}
+    out = []
+    for name in ("parareal_burgers_3d", "parareal_diffusion_2d_multi_iteration"):
+        case = cases.PARAREAL_BY_NAME[name]
+        if world not in case.sizes:
+            continue
+        ivp = case.build(ns)
+        p = Parareal(FDMOperator(kinds[case.f[0]](), TCD(), case.f[1]),
+                     FDMOperator(kinds[case.g[0]](), TCD(), case.g[1]), case.tol)
+        y = p.solve(ivp).discrete_y()
+        g = load_golden(name)
+        err = per_step_rel_err(y[g[f"steps_{world}"]], g[f"y_{world}"])
+        expected = int(g[f"iterations_{world}"])
+        out.append({
+            "case": f"{name}, P = {world}, NCCL, vs the reference's golden trajectory",
+            "max_rel_err": err, "tolerance": 1e-12,
+            "iterations": p.last_iterations, "iterations_expected": expected,
+            "ok": bool(err <= 1e-12 and p.last_iterations == expected),
+        })
+    # fused kernels + NCCL hand-off against the oracle's rank emulation
+    shape = (24, 28, 32)
+    eq = ns.BurgersEquation(3, 100.0)
+    mesh = ns.Mesh([(0.0, 1.0)] * 3, [1.0 / (m - 1) for m in shape])
+    bc = ns.NeumannBoundaryCondition(lambda x, t: np.zeros((len(x), 3)), is_static=True)
+    cp = ns.ConstrainedProblem(eq, mesh, [(bc, bc)] * 3)
+    rng = np.random.default_rng(17)
+    y0 = rng.uniform(-1.0, 1.0, shape + (3,))
+    d_t = 2e-5
+    ivp = ns.InitialValueProblem(cp, (0.0, world * 4 * d_t),
+                                 ns.DiscreteInitialCondition(cp, y0, True))
+    f = FDMOperator(RK4(), TCD(), d_t)
+    g = FDMOperator(FE(), TCD(), 2 * d_t)
+    p = Parareal(f, g, 1e-9)
+    y = p.solve(ivp).discrete_y()
+    plan = f.prepare(ivp)[-1]
+
+    def sub_ivp(cp_, interval, y_start):
+        return ns.InitialValueProblem(
+            cp_, interval, ns.DiscreteInitialCondition(cp_, y_start, True))
+
+    _, y_ref, its = oracle.parareal_solve(
+        ivp, oracle.OracleFDMOperator("rk4", d_t),
+        oracle.OracleFDMOperator("forward_euler", 2 * d_t), 1e-9, world, sub_ivp)
+    err = per_step_rel_err(y, y_ref)
+    out.append({
+        "case": f"Parareal 3-D Burgers {'x'.join(map(str, shape))}, P = {world}, "
+                "NCCL, vs oracle.parareal_solve",
+        "kernels": "fused stage pairs" if plan.fused is not None else "stage kernels",
+        "max_rel_err": err, "tolerance": 1e-12,
+        "iterations": p.last_iterations, "iterations_expected": int(its),
+        "ok": bool(err <= 1e-12 and p.last_iterations == its),
+    })
+    # slabs of axis 0 against the undecomposed solve (same kernels, one GPU)
+    shape = (16 * world, 24, 32)
+    mesh = ns.Mesh([(0.0, 1.0)] * 3, [1.0 / (m - 1) for m in shape])
+    cp = ns.ConstrainedProblem(eq, mesh, [(bc, bc)] * 3)
+    y0 = np.random.default_rng(19).uniform(-1.0, 1.0, shape + (3,))
+    ivp = ns.InitialValueProblem(cp, (0.0, 3 * d_t),
+                                 ns.DiscreteInitialCondition(cp, y0, True))
+    whole = FDMOperator(RK4(), TCD(), d_t).solve(ivp).discrete_y()
+    cut = FDMOperator(RK4(), TCD(), d_t)
+    cut.spatial_decomposition = True
+    y = cut.solve(ivp).discrete_y()
+    err = per_step_rel_err(y, whole)
+    out.append({
+        "case": f"slab-decomposed 3-D Burgers {'x'.join(map(str, shape))}, "
+                f"{world} slabs, NCCL halo exchange, vs the undecomposed solve",
+        "max_rel_err": err, "tolerance": 1e-14, "ok": bool(err <= 1e-14),
+    })
+    return out
+
+
+# ---------------------------------------------------------------------------
+# modelled DRAM traffic and the other named configurations
+# ---------------------------------------------------------------------------
+def _stencil_components(exprs):
+    """y components the given right-hand sides read (any leaf kind)."""
+    comps = set()
+    for e in exprs:
+        for sym in e.free_symbols:
+            tokens = sym.name.split("_")
+            kind, idx = tokens[0], [int(v) for v in tokens[1:]]
+            if kind in ("t", "x"):
+                continue
+            if kind in ("y", "y-gradient", "y-hessian", "y-laplacian"):
+                comps.add(idx[0])
+            elif kind == "y-divergence":
+                comps.update(idx)
+            elif kind == "y-curl":
+                comps.update(idx if len(idx) == 2 else idx[:-1])
+            elif kind == "y-vector-laplacian":
+                comps.update(idx[:-1])
+    return comps
+
+
+def modelled_bytes_per_cell_step(low, plan):
+    """Compulsory DRAM bytes per cell and RK4 step of the schedule the plan
+    runs (MODELLED from the plan, not measured: halo re-reads, boundary
+    tables and coordinate vectors are not counted).  Fused stage pairs move
+    7 doubles per time-stepped component (1+2: r y, w u3, w acc; 3+4: r u3,
+    r y, r acc, w y+).  Stage kernels move, per stage, every component a
+    right-hand side reads once, the step-start value and the accumulator of
+    the time-stepped components, and the stage's outputs; components that are
+    not time-stepped are read in place when the plan passes them through."""
+    dt = low.kind_indices("D_Y_OVER_D_T")
+    other = [i for i in range(low.y_dim) if i not in dt]
+    n_dt = len(dt)
+    if plan.fused is not None:
+        return 8 * 7 * n_dt
+    rhs_dt = [low.rhs[i] for i in dt]
+    rhs_aux = [low.rhs[i] for i in other]
+    read_dt = _stencil_components(rhs_dt)
+    read_first = read_dt | _stencil_components(rhs_aux) | set(dt)
+    passthrough = bool(plan.spec.passthrough)
+    carried = 0 if passthrough else len(other)  # copied through every stage
+    doubles = 0
+    # stage 1: reads y (all needed comps once), writes u, acc, aux outputs
+    doubles += len(read_first) + 2 * n_dt + len(other) + carried
+    # stages 2, 3: read stage input comps, y and acc of the dt comps; write u, acc
+    per_mid = len(read_dt | (set() if passthrough else set(other))) + 2 * n_dt
+    per_mid += 2 * n_dt + carried
+    # (dt comps that no right-hand side reads are not loaded as stencil input)
+    doubles += 2 * per_mid
+    # stage 4: as above without the u / acc writes
+    doubles += len(read_dt) + 2 * n_dt + n_dt
+    return 8 * doubles
+
+
+def run_workload_line(name, n, steps, warmup, args, ns, FDMOperator, RK4, TCD, dv,
+                      torch, peak):
+    """One bounded device-resident measurement of a named configuration."""
+    builder, _, y_dim, dims, label = WORKLOADS[name]
+    cells = n**dims
+    total = warmup + steps
+    ivp, d_t = builder(ns, n, total)
+    op = FDMOperator(RK4(), TCD(), d_t)
+    jacobi = name == "navier_stokes_2d"
+    if jacobi:
+        op.max_jacobi_sweeps = args.jacobi_sweeps
+        np.random.seed(0)
+    cp, t, y0, low, plan = op.prepare(ivp)
+    y_dev = dv.upload_state(y0, low.n_cells, low.y_dim)
+    traj = torch.empty((total, y_dim * cells), dtype=torch.float64, device="cuda")
+    op.integrate_on_device(cp, plan, y_dev, t[: warmup + 1], traj[:warmup])
+    torch.cuda.synchronize()
+    l0 = dv.total_launches()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    op.integrate_on_device(cp, plan, traj[warmup - 1], t[warmup:], traj[warmup:])
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    launches = (dv.total_launches() - l0) // steps
+    finite = bool(torch.isfinite(traj[-1]).all().item())
+    real = modelled_bytes_per_cell_step(low, plan)
+    alg = 128 * y_dim
+    line = {
+        "name": name, "workload": f"{label}, {'x'.join([str(n)] * dims)} mesh, RK4",
+        "value": cells / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms,
+        "steps": steps, "launches_per_step": launches,
+        "kernels": "fused stage pairs" if plan.fused is not None else "stage kernels",
+        "algorithmic_bytes_per_cell_step": alg,
+        "frac": alg * cells / (ms * 1e-3) / 1e9 / peak,
+        "modelled_bytes_per_cell_step": real,
+        "frac_real": real * cells / (ms * 1e-3) / 1e9 / peak,
+        "finite": finite,
+    }
+    if jacobi:
+        sweeps = float(np.mean(op.last_jacobi_sweeps))
+        line["jacobi_sweeps_per_step_cap"] = args.jacobi_sweeps
+        line["jacobi_sweeps_per_step"] = sweeps
+        line["note"] = ("ms_per_step = explicit stages + the capped Jacobi "
+                        "stream-function solve (the reference iterates to "
+                        "tolerance: not reference-matching at this size); frac "
+                        "counts 24 B per cell-sweep on top of the stages")
+        jb = 24 * sweeps
+        line["frac"] = (alg + jb) * cells / (ms * 1e-3) / 1e9 / peak
+        line["frac_real"] = (real + jb) * cells / (ms * 1e-3) / 1e9 / peak
+        # the Jacobi kernel alone: a fixed number of sweeps, tolerance 0
+        n_sw = 400
+        rhs = torch.zeros(cells, dtype=torch.float64, device="cuda")
+        init = torch.rand(cells, dtype=torch.float64, device="cuda")
+        out = torch.empty(y_dim * cells, dtype=torch.float64, device="cuda")
+        plan.jacobi(rhs, init, out, 0.0, 16)
+        torch.cuda.synchronize()
+        a.record()
+        done = plan.jacobi(rhs, init, out, 0.0, n_sw)
+        b.record()
+        torch.cuda.synchronize()
+        ms_sw = a.elapsed_time(b) / max(done, 1)
+        line["jacobi"] = {
+            "sweeps": done, "ms_per_sweep": ms_sw,
+            "value": cells / (ms_sw * 1e-3) / 1e9, "unit": "Gcell-sweeps/s",
+            "frac": 24 * cells / (ms_sw * 1e-3) / 1e9 / peak,
+            "bytes_per_cell_sweep": 24,
+        }
+    del traj, y_dev
+    torch.cuda.empty_cache()
+    return line
+
+
+def small_mesh_latency(ns, FDMOperator, RK4, TCD, torch):
+    """K1 (examples/diffusion_1d_fdm.py, 101 vertices, dynamic boundary
+    conditions) and the K2 example's fine solver (21 x 21): microseconds per
+    time step through ``FDMOperator.solve`` (single-block time loop)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from golden import cases
+
+    out = []
+    for label, ivp, d_t in (
+        ("K1 examples/diffusion_1d_fdm.py (101 vertices, dynamic BCs, T = 10)",
+         cases.diffusion_1d_dynamic(ns, 10.0), 0.0025),
+        ("K1 static-boundary twin", cases.diffusion_1d_static(ns, 10.0), 0.0025),
+        ("K2 example fine solver (21 x 21, T = 40, d_t = 1e-3)",
+         cases.diffusion_2d(ns, 40.0), 1e-3),
+    ):
+        op = FDMOperator(RK4(), TCD(), d_t)
+        op.solve(ivp)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sol = op.solve(ivp)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        n_steps = len(sol.t_coordinates)
+        out.append({"case": label, "steps": n_steps,
+                    "us_per_step": dt / n_steps * 1e6, "wall_s": dt})
+    return out
+
+
+# ---------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------
 def run_b200(args):
@@ -656,7 +976,15 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    TCD = ThreePointCentralDifferenceMethod
     if world == 1:
+        parity = None
+        if not args.no_parity:
+            try:
+                parity = parity_single_gpu(args, ns, FDMOperator, RK4, TCD, dv, torch)
+            except Exception as exc:  # the measured line must survive
+                parity = [{"error": f"{type(exc).__name__}: {str(exc)[:300]}", "ok": False}]
+            torch.cuda.empty_cache()
         # ---- device-resident RK4 steps --------------------------------
         total = args.warmup + args.steps
         ivp, d_t = builder(ns, n, total)
@@ -761,6 +1089,25 @@ def run_b200(args):
         profile = load_traffic()
         traffic = profile.get(f"{args.workload}_{n}_rk4_step_dram_bytes")
         kernels = profile.get(f"{args.workload}_{n}_kernels")
+        modelled = modelled_bytes_per_cell_step(low, plan)
+        workloads, latency = None, None
+        if not args.no_workloads and args.workload == "burgers_3d":
+            workloads = []
+            for w_name, w_n, w_steps in (
+                ("cahn_hilliard_3d", 256, 20), ("shallow_water_polar", 4096, 10),
+                ("navier_stokes_2d", 4096, 3), ("diffusion_2d", 2048, 50),
+            ):
+                try:
+                    workloads.append(run_workload_line(
+                        w_name, w_n, w_steps, 3, args, ns, FDMOperator, RK4, TCD,
+                        dv, torch, peak))
+                except Exception as exc:
+                    workloads.append({"name": w_name,
+                                      "error": f"{type(exc).__name__}: {str(exc)[:300]}"})
+            try:
+                latency = small_mesh_latency(ns, FDMOperator, RK4, TCD, torch)
+            except Exception as exc:
+                latency = [{"error": f"{type(exc).__name__}: {str(exc)[:300]}"}]
         line = {
             "metric": metric_name(args.workload, n),
             "value": value,
@@ -793,6 +1140,10 @@ def run_b200(args):
                 "traffic": traffic,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_cell_step": alg_bytes_step // cells,
+                "modelled_bytes_per_cell_step": modelled,
+                "frac_real_modelled": modelled * cells * args.steps / (ms * 1e-3) / 1e9 / peak,
+                "traffic_source": "ncu capture of an earlier run (profiles/traffic.json); "
+                                  "the modelled figure is computed from this run's plan",
                 "jacobi_sweeps_per_step": sweeps,
                 "scope": "one time step = all stage(-pair) launches of the "
                          "timed region; achieved = algorithmic bytes of a step "
@@ -804,11 +1155,22 @@ def run_b200(args):
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": launches,
+            "parity": parity,
+            "workloads": workloads,
+            "small_mesh_latency": latency,
         }
         print(json.dumps(line), flush=True)
         return
 
     # ---- N > 1: Parareal, one time slice per GPU ----------------------------
+    parity = None
+    if not args.no_parity:
+        try:
+            parity = parity_multi_gpu(world, rank, ns, FDMOperator, RK4,
+                                      ForwardEulerMethod, TCD, PararealOperator, torch)
+        except Exception as exc:  # the measured line must survive
+            parity = [{"error": f"{type(exc).__name__}: {str(exc)[:300]}", "ok": False}]
+        torch.cuda.empty_cache()
     s_steps = args.slice_steps
     total_steps = world * s_steps
     ivp, d_t = builder(ns, n, total_steps)
@@ -822,6 +1184,23 @@ def run_b200(args):
     y0_planes = dv.upload_state(
         ivp.initial_condition.discrete_y_0_view(True), cells, y_dim
     )
+    # the serial alternative: one GPU stepping the fine operator through one
+    # slice (x world slices); timed here on every rank, max over ranks
+    cp_f, _, _, low_f, plan_f = f.prepare(ivp)
+    t_slice = np.arange(s_steps + 1) * d_t
+    scratch = torch.empty((s_steps, y_dim * cells), dtype=torch.float64, device="cuda")
+    f.integrate_on_device(cp_f, plan_f, y0_planes, t_slice[:3], scratch[:2])
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    f.integrate_on_device(cp_f, plan_f, y0_planes, t_slice, scratch)
+    f1.record()
+    barrier()
+    fine_ms = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(fine_ms, op=dist.ReduceOp.MAX)
+    fine_slice_ms = float(fine_ms.item())
+    del scratch
+    torch.cuda.empty_cache()
     for _ in range(args.warmup):
         p.solve_on_device(ivp, y0_planes)
     barrier()
@@ -927,8 +1306,10 @@ def run_b200(args):
 
     if rank == 0:
         value = cells * total_steps * args.steps / (ms * 1e-3) / 1e9
+        wall_ms = ms / args.steps
+        serial_ms = fine_slice_ms * world
         line = {
-            "metric": metric_name(args.workload, n),
+            "metric": parareal_metric(args.workload, n),
             "value": value,
             "unit": UNIT,
             "n_gpus": world,
@@ -971,6 +1352,21 @@ def run_b200(args):
             "cpu_baseline": None,
             "e2e": e2e,
             "gpu_launches": launches,
+            "parareal": {
+                "wall_ms_per_solve": wall_ms,
+                "fine_slice_ms": fine_slice_ms,
+                "serial_fine_ms": serial_ms,
+                "speedup_vs_serial_fine": serial_ms / wall_ms,
+                "slices": world,
+                "fine_steps_per_slice": s_steps,
+                "iterations": iterations,
+                "bound_p_over_k": world / max(iterations, 1),
+                "note": "serial_fine_ms = the fine operator stepping all "
+                        f"{total_steps} steps on one GPU (the slice solve timed "
+                        "on every rank, max over ranks, x slices); the Parareal "
+                        "speed-up over it is bounded by P / K",
+            },
+            "parity": parity,
             "spatial_decomposition": spatial,
         }
         print(json.dumps(line), flush=True)

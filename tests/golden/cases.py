@@ -538,7 +538,8 @@ PARAREAL_CASES = [
     PararealCase(
         "parareal_diffusion_2d_multi_iteration",
         lambda ns: diffusion_2d(ns, t_end=0.8),
-        ("rk4", 2e-3), ("forward_euler", 5e-2), 1e-4, stride=20,
+        ("rk4", 2e-3), ("forward_euler", 5e-2), 1e-4, sizes=(1, 2, 4, 8),
+        stride=20,
     ),
     PararealCase(
         "parareal_lorenz",
@@ -549,7 +550,7 @@ PARAREAL_CASES = [
     PararealCase(
         "parareal_burgers_3d",
         lambda ns: burgers_3d_cartesian(ns, n=8, t_end=0.016),
-        ("rk4", 1e-3), ("forward_euler", 2e-3), 1e-6, sizes=(1, 2, 4),
+        ("rk4", 1e-3), ("forward_euler", 2e-3), 1e-6, sizes=(1, 2, 4, 8),
     ),
 ]
 
