@@ -27,10 +27,11 @@ typedef struct pml_plan_desc {
   int y_dim;        /* components of y */
   int n_dt, n_alg, n_lap; /* equations per LHS kind (differential_equation.py:140-149) */
   int block[3];     /* thread block shape the source was generated for */
-  int fused;        /* 1: the source has the fused stage-pair kernels */
+  int fused;        /* != 0: the source has the fused stage-pair kernels
+                       (1 = barrier per plane, 2 = warp-specialised pipeline) */
   int fused_tile[2]; /* their tile (cells along the contiguous axis, axis 1) */
   int fused_zc;     /* planes of the marching axis per thread block */
-  int fused_threads; /* threads per block (tile + halo 1, rounded to warps) */
+  int fused_threads; /* threads per block of the fused kernels */
   int fused_smem[2]; /* dynamic shared memory: stage 1+2 / midpoint, stage 3+4 */
   int small_threads; /* > 0: the source has the single-block time loop kernel */
   int zrep;         /* cells along axis 0 per thread in the stage kernels */
@@ -57,7 +58,7 @@ typedef struct pml_workspace {
   double* jac_a;     /* n_lap * n_cells */
   double* jac_b;     /* n_lap * n_cells */
   double* partials;  /* one double per thread block */
-  int* flags;        /* 2 ints: done, sweeps */
+  int* flags;        /* 3 ints: done, sweeps, block ticket of the sweep kernel */
   double* t_dev;     /* step start times for the single-block kernel */
   long long t_capacity; /* doubles available at t_dev */
 } pml_workspace;
@@ -89,6 +90,21 @@ int pml_fdm_run(pml_plan* plan, int integrator, const pml_workspace* ws,
                 double d_t, long long slot0, const double* jacobi_init_dev,
                 double jacobi_tol, long long max_sweeps, int* sweeps_out_host,
                 void* stream);
+
+/* The same for `batch` initial states of one problem over one time grid
+ * (the data generation of supervised_ml_operator.py:130-236 solves many
+ * perturbed sub-IVPs of a problem): member b reads y0_dev + b *
+ * y0_batch_stride and writes traj_dev + b * traj_batch_stride.  Small meshes
+ * run all members in ONE launch, one thread block per member, and need
+ * `batch` sets of scratch buffers (u_a, u_b, acc at member stride
+ * ws_batch_stride doubles); larger meshes run member after member.  Systems
+ * with Y_LAPLACIAN equations are not batched. */
+int pml_fdm_run_batch(pml_plan* plan, int integrator, const pml_workspace* ws,
+                      const double* y0_dev, double* traj_dev,
+                      long long traj_step_stride, int batch,
+                      long long y0_batch_stride, long long traj_batch_stride,
+                      long long ws_batch_stride, const double* t_host,
+                      int n_steps, double d_t, long long slot0, void* stream);
 
 /* The same time step one launch ("phase") at a time, for callers that
  * decompose the mesh into slabs of axis 0 and exchange halo planes between
@@ -137,6 +153,52 @@ int pml_parareal_update(const double* coarse_end_dev, const double* corr_dev,
 int pml_parareal_shift(double* traj_dev, long long n_steps,
                        long long step_stride, const double* new_end_dev,
                        double* delta_scratch_dev, long long n, void* stream);
+
+/* Device-side initial conditions (initial_condition.py:246-378): the state
+ * at t0 is evaluated on the mesh straight into component planes, so a 512^3
+ * Gaussian costs a millisecond instead of minutes of host NumPy.
+ * axis_dev[a]: mesh.vertex_axis_coordinates[a]; for curvilinear meshes
+ * trig_dev holds the host-evaluated cos / sin of the angular axes
+ * (cos(theta)[i1], sin(theta)[i1], sin(phi)[i2], cos(phi)[i2]) so that the
+ * Cartesian coordinates are the products mesh.py:to_cartesian_coordinates
+ * forms. */
+typedef struct pml_ic_mesh {
+  int n_dims;
+  int shape[3];
+  int coord;                  /* 0 cartesian, 1 polar, 2 cylindrical, 3 spherical */
+  const double* axis_dev[3];
+  const double* trig_dev[4];
+} pml_ic_mesh;
+
+#define PML_IC_MAX_COMPONENTS 16
+/* One multivariate normal density per component (GaussianInitialCondition,
+ * initial_condition.py:300-343; scipy.stats.multivariate_normal.pdf):
+ * exp(-0.5 (log_norm + |(x - mean) U|^2)) * multiplier with the whitening
+ * matrix U (row-major x_dim x x_dim) and log_norm = rank log(2 pi) +
+ * log pdet(cov), both computed by the host from the covariance like SciPy. */
+typedef struct pml_ic_gaussian_params {
+  double mean[3];
+  double whiten[9];
+  double log_norm;
+  double multiplier;
+} pml_ic_gaussian_params;
+int pml_ic_gaussian(const pml_ic_mesh* mesh, int y_dim,
+                    const pml_ic_gaussian_params* params_host,
+                    double* planes_dev, void* stream);
+/* Product over the mesh axes of per-axis factor vectors (Cartesian meshes:
+ * MarginalBetaProductInitialCondition, initial_condition.py:346-378, with the
+ * 1-D Beta densities evaluated by the host): planes[c][cell] =
+ * ((f[c][0][i0] * f[c][1][i1]) * f[c][2][i2]) * multiplier[c];
+ * factors_dev[c * n_dims + a] is a device vector of shape[a] doubles. */
+int pml_ic_separable(const pml_ic_mesh* mesh, int y_dim,
+                     const double* const* factors_dev_host,
+                     const double* multipliers_host, double* planes_dev,
+                     void* stream);
+/* Overwrites the constrained boundary vertices of component planes with the
+ * plan's static Dirichlet tables, later axes winning at shared edges
+ * (initial_condition.py:86-89, constrained_problem.py:286-295). */
+int pml_apply_dirichlet(pml_plan* plan, double* planes_dev, long long slot,
+                        void* stream);
 
 #ifdef __cplusplus
 }

@@ -67,8 +67,40 @@ class Workspace(Structure):
     ]
 
 
+IC_MAX_COMPONENTS = 16
+
+
+class IcMesh(Structure):
+    _fields_ = [
+        ("n_dims", c_int),
+        ("shape", c_int * 3),
+        ("coord", c_int),
+        ("axis_dev", c_void_p * 3),
+        ("trig_dev", c_void_p * 4),
+    ]
+
+
+class IcGaussianParams(Structure):
+    _fields_ = [
+        ("mean", c_double * 3),
+        ("whiten", c_double * 9),
+        ("log_norm", c_double),
+        ("multiplier", c_double),
+    ]
+
+
 # every symbol declared in include/pararealml_b200.h
 SYMBOLS = {
+    "pml_ic_gaussian": (
+        c_int,
+        [POINTER(IcMesh), c_int, POINTER(IcGaussianParams), c_void_p, c_void_p],
+    ),
+    "pml_ic_separable": (
+        c_int,
+        [POINTER(IcMesh), c_int, POINTER(c_void_p), POINTER(c_double), c_void_p,
+         c_void_p],
+    ),
+    "pml_apply_dirichlet": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p]),
     "pml_last_error": (c_char_p, []),
     "pml_version": (c_int, []),
     "pml_plan_create": (
@@ -85,6 +117,14 @@ SYMBOLS = {
             c_void_p, c_int, POINTER(Workspace), c_void_p, c_void_p,
             c_longlong, POINTER(c_double), c_int, c_double, c_longlong,
             c_void_p, c_double, c_longlong, POINTER(c_int), c_void_p,
+        ],
+    ),
+    "pml_fdm_run_batch": (
+        c_int,
+        [
+            c_void_p, c_int, POINTER(Workspace), c_void_p, c_void_p,
+            c_longlong, c_int, c_longlong, c_longlong, c_longlong,
+            POINTER(c_double), c_int, c_double, c_longlong, c_void_p,
         ],
     ),
     "pml_fdm_phase_count": (c_int, [c_void_p, c_int]),

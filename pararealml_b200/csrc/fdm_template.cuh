@@ -690,6 +690,7 @@ __device__ __forceinline__ int pml_inplane_path(bool active, int i1, int i2) {
   return 0;
 }
 
+#if PML_FUSED == 1
 template <int MODE>
 __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
                                                double* smem,
@@ -1021,7 +1022,399 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
 PML_FUSED_KERNEL(pml_fused_rk4_12, PML_F_RK4_12)
 PML_FUSED_KERNEL(pml_fused_rk4_34, PML_F_RK4_34)
 PML_FUSED_KERNEL(pml_fused_mid, PML_F_MID)
+#endif  // PML_FUSED == 1
 #endif  // PML_FUSED
+
+// ---------------------------------------------------------------------------
+// Fused stage pairs, warp-specialised (PML_FUSED == 2): the same temporal
+// blocking as above, organised as a three-role pipeline inside one thread
+// block, coupled only by mbarriers (no __syncthreads in the plane loop):
+//
+//   loader warp   one lane issues the TMA boxes of every plane of stage A's
+//                 stencil input into a shared-memory ring, as soon as the
+//                 consumers have released the slot (the pointwise operands --
+//                 step-start value, accumulator -- are plain coalesced loads
+//                 of the compute warps, issued ahead of their barrier waits);
+//   A warps       one warp per 32 cells of a row of the stage-A tile (tile +
+//                 halo 1): stage A on plane p from the input ring, result to
+//                 the "mid" ring, its increment K to the "k" ring;
+//   B warps       one warp per 32 cells of a row of the tile: stage B on plane
+//                 p from the mid ring (needs planes p-1..p+1 of stage A),
+//                 outputs straight to HBM.
+//
+// Both compute roles march along axis 0 and keep the three values of their own
+// cell column (planes p-1, p, p+1) in registers, so a 7-point stencil costs 5
+// shared-memory loads per component instead of 7.  Every role runs at its own
+// pace: the A warps may lead the B warps by PML_WS_SMID - 2 planes, the loader
+// the A warps by the depth of the input ring.  Plane bookkeeping is in "steps"
+// r = plane - (zb - 2) of the chunk [zb, ze): the loader handles r = 0 ..
+// nB + 3, stage A r = 1 .. nB + 2, stage B r = 2 .. nB + 1; planes outside the
+// mesh are no-ops that still signal, so barrier slot r & 7 is in phase r >> 3
+// for every role.
+//   full[r & 7]   TMA bytes of loader step r (input plane r) have landed
+//   adone[r & 7]  every A warp has finished plane r
+//   bdone[r & 7]  every B warp has finished plane r
+// ---------------------------------------------------------------------------
+#if PML_FUSED == 2
+#define PML_WPR (PML_MW / 32)            // warps per row of the stage-A tile
+#define PML_NAW (PML_WPR * PML_MH)       // stage-A warps
+#define PML_NBW (PML_WPR * PML_FTY)      // stage-B warps
+#define PML_WS_THREADS (32 * (1 + PML_NAW + PML_NBW))
+static_assert(PML_MW % 32 == 0, "stage-A tile rows are whole warps");
+static_assert(PML_WS_THREADS == PML_F_THREADS, "thread count of the plan");
+
+// stencil source of a marching warp: the cell's own column (planes p-1, p,
+// p+1) is in registers, everything else is read from the ring
+template <int PITCH, int PLANE>
+struct PmlMarchSrc {
+  const double* base[3];
+  const double* y;  // passthrough components are read from the state itself
+  double v[PML_NRING][3];
+  template <int D0, int D1, int D2>
+  __device__ __forceinline__ double rel(int comp, const PmlCell& c) const {
+    if (PML_PASSTHROUGH && PML_KIND[comp] != 0) {
+      constexpr i64 off =
+          D0 * PmlAx<0>::S + D1 * PmlAx<1>::S + D2 * PmlAx<2>::S;
+      return PML_LD(y + (i64)comp * PML_NCELLS + c.idx + off);
+    }
+    if (D1 == 0 && D2 == 0) return v[pml_ring_index(comp)][D0 + 1];
+#if PML_NDIM == 3
+    return base[D0 + 1][pml_ring_index(comp) * PLANE + D1 * PITCH + D2];
+#else
+    return base[D0 + 1][pml_ring_index(comp) * PLANE + D1];
+#endif
+  }
+};
+
+__device__ __forceinline__ void pml_mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// waits for the phase of barrier slot (r & 7) that step / plane r completes
+__device__ __forceinline__ void pml_ws_wait(unsigned bars, int r) {
+  const unsigned addr = bars + ((unsigned)r & 7u) * 8u;
+  const unsigned parity = ((unsigned)r >> 3) & 1u;
+  unsigned ok, spins = 0;
+  do {
+    asm volatile(
+        "{\n"
+        "  .reg .pred p;\n"
+        "  mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "  selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity), "r"(0x989680u)  // suspend-time hint (ns)
+        : "memory");
+    // a protocol error must end the launch, not hang the device
+    if (!ok && ++spins > (1u << 22)) __trap();
+  } while (!ok);
+}
+
+template <int MODE>
+__device__ __forceinline__ void pml_ws_body(const PmlFusedArgs& f, double* smem,
+                                            unsigned long long* bars) {
+  const PmlArgs& a = f.s;
+  constexpr bool first = MODE != PML_F_RK4_34;      // stage A's input is y itself
+  constexpr bool pointwise = MODE == PML_F_RK4_34;  // needs y and acc per cell
+  constexpr int NK = PML_NDT > 0 ? PML_NDT : 1;
+  constexpr int S_IN = PML_WS_SIN, S_MID = PML_WS_SMID, S_K = PML_WS_SK;
+  static_assert(S_IN >= 4 && S_IN <= 8 && S_MID >= 3 && S_MID <= 8, "ring depths");
+  static_assert(S_K >= S_MID - 1 && S_K <= 8, "k ring covers the A/B lead");
+  constexpr int IN_SLOT = PML_NRING * PML_IN_PLANE;
+  constexpr int MID_SLOT = PML_NRING * PML_MID_PLANE;
+  constexpr int K_SLOT = NK * PML_OWN_PLANE;
+  // the TMA destination first (128-byte aligned: planes are padded to 16 doubles)
+  double* in_ring = smem;
+  double* mid_ring = in_ring + S_IN * IN_SLOT;
+  double* k_ring = mid_ring + S_MID * MID_SLOT;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ox = blockIdx.x * PML_FTX;  // mesh coordinates of the tile origin
+#if PML_NDIM == 3
+  const int oy = blockIdx.y * PML_FTY;
+  const int chunk = blockIdx.z;
+#else
+  const int oy = 0;
+  const int chunk = blockIdx.y;
+#endif
+  const int zb = chunk * PML_FZC;
+  const int ze = min(zb + PML_FZC, PML_N0);
+  const int nB = ze - zb;
+  const int a_lo = max(zb - 1, 0), a_hi = min(ze, PML_N0 - 1);
+  const int in_lo = max(zb - 2, 0), in_hi = min(ze + 1, PML_N0 - 1);
+  const unsigned full_s = pml_smem_addr(bars);
+  const unsigned adone_s = full_s + 64u, bdone_s = full_s + 128u;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      pml_mbar_init(full_s + k * 8u, 1);
+      pml_mbar_init(adone_s + k * 8u, PML_NAW);
+      pml_mbar_init(bdone_s + k * 8u, PML_NBW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // =========================== loader ====================================
+  if (warp == 0) {
+    if (lane != 0) return;
+    constexpr unsigned IN_BOX_BYTES = PML_IW * PML_IH * 8;
+    const unsigned in_s = pml_smem_addr(in_ring);
+    unsigned s_in = 0;
+#pragma unroll 1
+    for (int r = 0; r < nB + 4; ++r) {
+      const int p = zb - 2 + r;
+      // the slot was last read by stage A of plane r - S_IN + 1
+      if (r - S_IN + 1 >= 1) pml_ws_wait(adone_s, r - S_IN + 1);
+      const unsigned bar = full_s + ((unsigned)r & 7u) * 8u;
+      if (p >= in_lo && p <= in_hi) {
+        pml_mbar_expect_tx(bar, PML_NRING * IN_BOX_BYTES);
+#pragma unroll
+        for (int k = 0; k < PML_C; ++k)
+          if (!PML_PASSTHROUGH || PML_KIND[k] == 0)
+            pml_tma_box(in_s + (s_in * IN_SLOT + pml_ring_index(k) * PML_IN_PLANE) * 8u,
+                        f.tm_in, ox - 2, oy - 2 * PML_FHY, p, k, bar);
+      } else {
+        pml_mbar_arrive(bar);
+      }
+      if (++s_in == S_IN) s_in = 0;
+    }
+    return;
+  }
+
+  // ============== compute roles: this lane's cell column ===================
+  const bool role_a = warp <= PML_NAW;
+  const int w = role_a ? warp - 1 : warp - 1 - PML_NAW;
+  const int mr = role_a ? w / PML_WPR : PML_FHY + w / PML_WPR;  // row in the A tile
+  const int mc = (w % PML_WPR) * 32 + lane;
+#if PML_NDIM == 3
+  const int i1 = oy - 1 + mr, i2 = ox - 1 + mc;
+  const bool in_plane = i1 >= 0 && i1 < PML_N1 && i2 >= 0 && i2 < PML_N2;
+  const bool owner = in_plane && mc >= 1 && mc <= PML_FTX && mr >= 1 && mr <= PML_FTY;
+  const int in_cell = (mr + 1) * PML_IW + (mc + 1);
+  const int own_cell = (mr - 1) * PML_FTX + (mc - 1);
+#else
+  const int i1 = ox - 1 + mc, i2 = 0;
+  const bool in_plane = i1 >= 0 && i1 < PML_N1;
+  const bool owner = in_plane && mc >= 1 && mc <= PML_FTX;
+  const int in_cell = mc + 1;
+  const int own_cell = mc - 1;
+#endif
+  const int mid_cell = mr * PML_MW + mc;
+  const i64 idx0 = pml_lin(0, in_plane ? i1 : 0, in_plane ? i2 : 0);
+
+  if (role_a) {
+    // ============================ stage A =================================
+    const int path_in0 = pml_inplane_path(in_plane, i1, i2);
+    PmlMarchSrc<PML_IW, PML_IN_PLANE> src;
+    src.y = a.y;
+    // stage A has no plane 0: the slot's first phase is completed here so
+    // that slot r & 7 is in phase r >> 3 for every plane r
+    if (lane == 0) pml_mbar_arrive(adone_s);
+    // input planes 0 and 1 (steps 0, 1): the column's first two values
+    pml_ws_wait(full_s, 0);
+    pml_ws_wait(full_s, 1);
+#pragma unroll
+    for (int q = 0; q < PML_NRING; ++q) {
+      src.v[q][0] = 0.0;
+      src.v[q][1] = in_ring[q * PML_IN_PLANE + in_cell];
+      src.v[q][2] = in_ring[IN_SLOT + q * PML_IN_PLANE + in_cell];
+    }
+    unsigned s_lo = 0, s_c = 1, s_hi = 2;   // input slots of planes r-1, r, r+1
+    unsigned s_m = 1 % S_MID, s_k = 1 % S_K;  // slots of plane r
+#pragma unroll 1
+    for (int r = 1; r <= nB + 2; ++r) {
+      const int p = zb - 2 + r;
+      const bool active = in_plane && p >= a_lo && p <= a_hi;
+      // stages 3+4: the step-start value comes straight from HBM / L2,
+      // requested before the waits so that it has arrived by the time the
+      // right-hand side is done
+      double y_start[NK];
+      if (pointwise && active) {
+#pragma unroll
+        for (int j = 0; j < PML_NDT; ++j)
+          y_start[j] = PML_LD_ONCE(a.y + (i64)PML_DT_IDX[j] * PML_NCELLS + idx0 +
+                                   (i64)p * PmlAx<0>::S);
+      }
+      pml_ws_wait(full_s, r + 1);
+#pragma unroll
+      for (int q = 0; q < PML_NRING; ++q) {
+        src.v[q][0] = src.v[q][1];
+        src.v[q][1] = src.v[q][2];
+        src.v[q][2] = in_ring[s_hi * IN_SLOT + q * PML_IN_PLANE + in_cell];
+      }
+      // the mid / k slots of plane r were last read by stage B of plane
+      // r - S_MID + 1 (k: r - S_K, not later)
+      if (r - S_MID + 1 >= 2) pml_ws_wait(bdone_s, r - S_MID + 1);
+      if (active) {
+        const int path = (p > 0 && p < PML_N0 - 1) ? path_in0 : 0;
+        PmlCell c;
+        c.i0 = p;
+        c.i1 = i1;
+        c.i2 = i2;
+        c.idx = idx0 + (i64)p * PmlAx<0>::S;
+        src.base[0] = in_ring + s_lo * IN_SLOT + in_cell;
+        src.base[1] = in_ring + s_c * IN_SLOT + in_cell;
+        src.base[2] = in_ring + s_hi * IN_SLOT + in_cell;
+        double K[NK];
+        pml_eval_dt(path, a, src, c, a.t_eval, K);
+        double* slot = mid_ring + s_m * MID_SLOT + mid_cell;
+        double* kslot = k_ring + s_k * K_SLOT + own_cell;
+#pragma unroll
+        for (int j = 0; j < PML_NDT; ++j) {
+          const int k = PML_DT_IDX[j];
+          const double y0 = first ? src.template rel<0, 0, 0>(k, c) : y_start[j];
+          double ua, kk = 0.0;
+          if (MODE == PML_F_MID) {
+            ua = y0 + (a.dt / 2.0) * K[j];
+          } else {
+            kk = a.dt * K[j];
+            ua = MODE == PML_F_RK4_12 ? y0 + kk / 2.0 : y0 + kk;
+          }
+          slot[pml_ring_index(k) * PML_MID_PLANE] = pml_dirichlet(a.dir, k, c, ua);
+          if (MODE != PML_F_MID && owner) kslot[j * PML_OWN_PLANE] = kk;
+        }
+#if PML_NALG + PML_NLAP > 0
+        if (!PML_PASSTHROUGH) {
+#pragma unroll
+          for (int k = 0; k < PML_C; ++k) {
+            if (PML_KIND[k] == 0) continue;
+            slot[k * PML_MID_PLANE] = pml_dirichlet(
+                a.dir, k, c, PML_LD(a.y + (i64)k * PML_NCELLS + c.idx));
+          }
+        }
+        if (first && owner && p >= zb && p < ze)
+          pml_first_stage_extras(path, a, src, c);
+#endif
+      }
+      __syncwarp();
+      if (lane == 0) pml_mbar_arrive(adone_s + ((unsigned)r & 7u) * 8u);
+      s_lo = s_c;
+      s_c = s_hi;
+      if (++s_hi == S_IN) s_hi = 0;
+      if (++s_m == S_MID) s_m = 0;
+      if (++s_k == S_K) s_k = 0;
+    }
+    return;
+  }
+
+  // ============================== stage B ===================================
+  PmlArgs b = a;  // stage B sees its own time and table slots
+  b.t_eval = f.t_eval_b;
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    b.neu[q] = f.neu_b[q];
+    b.dir[q] = f.dir_b[q];
+  }
+  const int path_in0 = pml_inplane_path(owner, i1, i2);
+  PmlMarchSrc<PML_MW, PML_MID_PLANE> src;
+  src.y = a.y;
+  if (lane == 0) {  // stage B has no planes 0 and 1 (see stage A)
+    pml_mbar_arrive(bdone_s);
+    pml_mbar_arrive(bdone_s + 8u);
+  }
+  pml_ws_wait(adone_s, 1);
+  pml_ws_wait(adone_s, 2);
+#pragma unroll
+  for (int q = 0; q < PML_NRING; ++q) {
+    src.v[q][0] = 0.0;
+    src.v[q][1] = mid_ring[(1 % S_MID) * MID_SLOT + q * PML_MID_PLANE + mid_cell];
+    src.v[q][2] = mid_ring[(2 % S_MID) * MID_SLOT + q * PML_MID_PLANE + mid_cell];
+  }
+  unsigned s_lo = 1 % S_MID, s_c = 2 % S_MID, s_hi = 3 % S_MID;  // mid slots r-1, r, r+1
+  unsigned s_k = 2 % S_K;                                        // k slot of plane r
+  const i64 cell0 = idx0 + (i64)zb * PmlAx<0>::S;
+  const double* y_at = b.y + cell0;            // step-start state at this cell
+  const double* acc_at = b.acc_in + cell0;
+  double* out_a = (MODE == PML_F_RK4_12 ? b.u_out : b.y_next) + cell0;
+  double* out_b = b.acc_out + cell0;
+#pragma unroll 1
+  for (int r = 2; r <= nB + 1; ++r) {
+    const int p = zb - 2 + r;
+    // pointwise operands straight from HBM / L2 (the step-start value was
+    // fetched for stage A a few planes ago): requested before the wait
+    double y_start[NK], acc_old[NK];
+    if (owner) {
+#pragma unroll
+      for (int j = 0; j < PML_NDT; ++j) {
+        const i64 o = (i64)PML_DT_IDX[j] * PML_NCELLS;
+        y_start[j] = PML_LD_ONCE(y_at + o);
+        acc_old[j] = pointwise ? PML_LD_ONCE(acc_at + o) : 0.0;
+      }
+    }
+    pml_ws_wait(adone_s, r + 1);
+#pragma unroll
+    for (int q = 0; q < PML_NRING; ++q) {
+      src.v[q][0] = src.v[q][1];
+      src.v[q][1] = src.v[q][2];
+      src.v[q][2] = mid_ring[s_hi * MID_SLOT + q * PML_MID_PLANE + mid_cell];
+    }
+    if (owner) {
+      const int path = (p > 0 && p < PML_N0 - 1) ? path_in0 : 0;
+      PmlCell c;
+      c.i0 = p;
+      c.i1 = i1;
+      c.i2 = i2;
+      c.idx = idx0 + (i64)p * PmlAx<0>::S;
+      src.base[0] = mid_ring + s_lo * MID_SLOT + mid_cell;
+      src.base[1] = mid_ring + s_c * MID_SLOT + mid_cell;
+      src.base[2] = mid_ring + s_hi * MID_SLOT + mid_cell;
+      double K[NK];
+      pml_eval_dt(path, b, src, c, b.t_eval, K);
+      const double* kr = k_ring + s_k * K_SLOT + own_cell;
+#pragma unroll
+      for (int j = 0; j < PML_NDT; ++j) {
+        const int k = PML_DT_IDX[j];
+        const i64 o = (i64)k * PML_NCELLS;
+        const double y0 = y_start[j];
+        if (MODE == PML_F_RK4_12) {
+          const double kk = b.dt * K[j];
+          PML_ST(out_b + o, kr[j * PML_OWN_PLANE] + 2.0 * kk);
+          PML_ST(out_a + o, pml_dirichlet(b.dir, k, c, y0 + kk / 2.0));
+        } else if (MODE == PML_F_RK4_34) {
+          const double kk = b.dt * K[j];
+          const double acc = acc_old[j] + 2.0 * kr[j * PML_OWN_PLANE];
+          PML_ST(out_a + o, pml_dirichlet(b.dir, k, c, y0 + pml_div6(acc + kk)));
+        } else {
+          PML_ST(out_a + o, pml_dirichlet(b.dir, k, c, y0 + b.dt * K[j]));
+        }
+      }
+#if PML_NALG + PML_NLAP > 0
+      if (MODE == PML_F_RK4_12 && !PML_PASSTHROUGH) {
+#pragma unroll
+        for (int k = 0; k < PML_C; ++k) {
+          if (PML_KIND[k] == 0) continue;
+          const i64 o = (i64)k * PML_NCELLS + c.idx;
+          b.u_out[o] = pml_dirichlet(b.dir, k, c, PML_LD(b.y + o));
+        }
+      }
+#endif
+    }
+    __syncwarp();
+    if (lane == 0) pml_mbar_arrive(bdone_s + ((unsigned)r & 7u) * 8u);
+    y_at += PmlAx<0>::S;
+    acc_at += PmlAx<0>::S;
+    out_a += PmlAx<0>::S;
+    out_b += PmlAx<0>::S;
+    s_lo = s_c;
+    s_c = s_hi;
+    if (++s_hi == S_MID) s_hi = 0;
+    if (++s_k == S_K) s_k = 0;
+  }
+}
+
+#define PML_WS_KERNEL(NAME, MODE)                                             \
+  extern "C" __global__ void __launch_bounds__(PML_F_THREADS, PML_FMIN_BLOCKS) \
+      NAME(const __grid_constant__ PmlFusedArgs f) {                         \
+    extern __shared__ __align__(128) double pml_ring[];                       \
+    __shared__ unsigned long long pml_bars[24];                               \
+    pml_ws_body<MODE>(f, pml_ring, pml_bars);                                 \
+  }
+
+PML_WS_KERNEL(pml_fused_rk4_12, PML_F_RK4_12)
+PML_WS_KERNEL(pml_fused_rk4_34, PML_F_RK4_34)
+PML_WS_KERNEL(pml_fused_mid, PML_F_MID)
+#endif  // PML_FUSED == 2
 
 // ---------------------------------------------------------------------------
 // Small meshes (and ODE systems): the whole time loop in ONE thread block.
@@ -1044,6 +1437,11 @@ struct PmlSmallArgs {
   double* u_a;
   double* u_b;
   double* acc;
+  // batched solves: thread block b integrates member b (same problem, same
+  // time grid); doubles between consecutive members
+  i64 y_batch_stride;
+  i64 traj_batch_stride;
+  i64 ws_batch_stride;
 };
 
 template <int STAGE>
@@ -1076,7 +1474,15 @@ __device__ __forceinline__ void pml_small_set(PmlArgs& a,
 }
 
 extern "C" __global__ void __launch_bounds__(PML_SMALL_THREADS)
-    pml_small_run(const __grid_constant__ PmlSmallArgs f) {
+    pml_small_run(const __grid_constant__ PmlSmallArgs g) {
+  // this block's member of the batch
+  PmlSmallArgs f = g;
+  const i64 member = blockIdx.x;
+  f.s.y = g.s.y + member * g.y_batch_stride;
+  f.traj = g.traj + member * g.traj_batch_stride;
+  f.u_a = g.u_a + member * g.ws_batch_stride;
+  f.u_b = g.u_b + member * g.ws_batch_stride;
+  f.acc = g.acc + member * g.ws_batch_stride;
   PmlArgs a = f.s;
   a.acc_in = f.acc;
   a.acc_out = f.acc;
@@ -1127,6 +1533,20 @@ extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ)
   for (int j = 0; j < PML_NDT; ++j) a.u_out[(i64)j * PML_NCELLS + c.idx] = K[j];
 }
 
+// static Dirichlet values written into component planes (device-side initial
+// conditions; initial_condition.py:86-89)
+extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ)
+    pml_apply_dirichlet_planes(const __grid_constant__ PmlArgs a) {
+  PmlCell c;
+  if (!pml_this_cell(c)) return;
+  if (pml_interior_mask(c) == PML_IM_ALL) return;
+#pragma unroll
+  for (int k = 0; k < PML_C; ++k) {
+    double* q = a.u_out + (i64)k * PML_NCELLS + c.idx;
+    *q = pml_dirichlet(a.dir, k, c, *q);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Jacobi anti-Laplacian for the LHS.Y_LAPLACIAN components
 // (numerical_differentiator.py:872-927, 1097-1186).  Component j of the Jacobi
@@ -1139,7 +1559,9 @@ struct PmlJacobiArgs {
   const double* rhs;       // NLAP planes
   double* y_new;           // NLAP planes
   double* partials;        // one partial sum of squares per block
-  const int* done;         // set once ||y_new - y_hat|| <= tol
+  int* flags;              // [0] done: set once ||y_new - y_hat|| <= tol,
+                           // [1] sweeps executed, [2] block ticket
+  double tol;
 };
 
 // start: channels-last (cell, NLAP) host draw -> planes, Dirichlet applied
@@ -1241,7 +1663,7 @@ __device__ __forceinline__ double pml_jacobi_cell_update(const PmlJacobiArgs& j,
 
 extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ)
     pml_jacobi_sweep(const __grid_constant__ PmlJacobiArgs j) {
-  if (*(const volatile int*)j.done) return;
+  if (*(const volatile int*)j.flags) return;
   double sq = 0.0;
 #pragma unroll
   for (int rep = 0; rep < (PML_NDIM <= 1 ? 1 : PML_JREP); ++rep) {
@@ -1259,32 +1681,40 @@ extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ)
   for (int off = 16; off > 0; off >>= 1) sq += __shfl_down_sync(0xffffffffu, sq, off);
   if ((tid & 31) == 0) red[tid >> 5] = sq;
   __syncthreads();
+  __shared__ int last_block;
+  const int n_blocks = (int)(gridDim.x * gridDim.y * gridDim.z);
   if (tid == 0) {
     double s = 0.0;
     const int nw = (PML_BX * PML_BY * PML_BZ + 31) / 32;
     for (int w = 0; w < nw; ++w) s += red[w];
     const i64 b = ((i64)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
     j.partials[b] = s;
+    // the block that takes the last ticket finishes the norm (the sweep and
+    // its convergence test are one launch; numerical_differentiator.py:917-925)
+    __threadfence();
+    last_block = atomicAdd(j.flags + 2, 1) == n_blocks - 1;
   }
-}
-
-// one block: sums the partials in a fixed order and raises the done flag
-extern "C" __global__ void __launch_bounds__(256)
-    pml_jacobi_check(const double* __restrict__ partials, int n_partials,
-                     double tol, int* done, int* sweeps) {
-  if (*(volatile int*)done) return;
-  __shared__ double red[256];
-  double s = 0.0;
-  for (int i = threadIdx.x; i < n_partials; i += 256) s += partials[i];
-  red[threadIdx.x] = s;
+  __syncthreads();
+  if (!last_block) return;
+  __threadfence();
+  // fixed summation order (256 strided lanes, then a tree): the norm does not
+  // depend on which block came last
+  constexpr int NT = PML_BX * PML_BY * PML_BZ;
+  __shared__ double lanes[256];
+  for (int v = tid; v < 256; v += NT) {
+    double s = 0.0;
+    for (int i = v; i < n_blocks; i += 256) s += __ldcg(j.partials + i);
+    lanes[v] = s;
+  }
   __syncthreads();
   for (int off = 128; off > 0; off >>= 1) {
-    if (threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+    for (int v = tid; v < off; v += NT) lanes[v] += lanes[v + off];
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    *sweeps += 1;
-    if (!(sqrt(red[0]) > tol)) *done = 1;
+  if (tid == 0) {
+    j.flags[1] += 1;
+    j.flags[2] = 0;
+    if (!(sqrt(lanes[0]) > j.tol)) j.flags[0] = 1;
   }
 }
 

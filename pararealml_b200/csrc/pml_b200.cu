@@ -142,6 +142,9 @@ struct PmlSmallArgs {
   double* u_a;
   double* u_b;
   double* acc;
+  long long y_batch_stride;
+  long long traj_batch_stride;
+  long long ws_batch_stride;
 };
 
 struct PmlJacobiArgs {
@@ -150,7 +153,8 @@ struct PmlJacobiArgs {
   const double* rhs;
   double* y_new;
   double* partials;
-  const int* done;
+  int* flags;
+  double tol;
 };
 
 // `name` is the file name recorded in the line info; when it is a real path the
@@ -215,8 +219,8 @@ struct pml_plan {
   unsigned fsmem[3] = {0, 0, 0};
   CUfunction small_run = nullptr;
   CUfunction eval_rhs = nullptr;
-  CUfunction jac_init = nullptr, jac_sweep = nullptr, jac_check = nullptr,
-             jac_store = nullptr;
+  CUfunction apply_dir = nullptr;
+  CUfunction jac_init = nullptr, jac_sweep = nullptr, jac_store = nullptr;
   pml_tables tables{};
   dim3 grid, block;
   dim3 sgrid;  // grid of the stage kernels (zrep cells along axis 0 per thread)
@@ -280,7 +284,7 @@ int jacobi_solve(pml_plan* p, const pml_workspace* ws, const PmlArgs& tbl,
                  double tol, long long max_sweeps, int* sweeps_out,
                  CUstream s) {
   // tbl carries the slots of t + dt for both Neumann and Dirichlet tables
-  PML_CUDA(cudaMemsetAsync(ws->flags, 0, 2 * sizeof(int), (cudaStream_t)s));
+  PML_CUDA(cudaMemsetAsync(ws->flags, 0, 3 * sizeof(int), (cudaStream_t)s));
   {
     PmlArgs a = tbl;
     const double* init = y_init;
@@ -291,8 +295,9 @@ int jacobi_solve(pml_plan* p, const pml_workspace* ws, const PmlArgs& tbl,
   double* bufs[2] = {ws->jac_a, ws->jac_b};
   long long issued = 0;
   int host_flags[2] = {0, 0};
-  long long batch = 16;
-  int n_partials = (int)((long long)p->jgrid.x * p->jgrid.y * p->jgrid.z);
+  // sweeps are enqueued in growing batches; after each batch the host reads
+  // the convergence flag (launches after convergence return at once)
+  long long batch = 32;
   while (true) {
     long long todo = batch;
     if (max_sweeps > 0 && issued + todo > max_sweeps) todo = max_sweeps - issued;
@@ -304,17 +309,11 @@ int jacobi_solve(pml_plan* p, const pml_workspace* ws, const PmlArgs& tbl,
       j.rhs = rhs;
       j.y_new = bufs[(issued + 1) & 1];
       j.partials = ws->partials;
-      j.done = ws->flags;
+      j.flags = ws->flags;
+      j.tol = tol;
       void* params[] = {&j};
       PML_CU(g_drv.launchKernel(p->jac_sweep, p->jgrid.x, p->jgrid.y, p->jgrid.z,
                                 p->block.x, p->block.y, p->block.z, 0, s, params,
-                                nullptr));
-      p->launches += 1;
-      const double* partials = ws->partials;
-      int* done = ws->flags;
-      int* sweeps = ws->flags + 1;
-      void* cparams[] = {&partials, &n_partials, &tol, &done, &sweeps};
-      PML_CU(g_drv.launchKernel(p->jac_check, 1, 1, 1, 256, 1, 1, 0, s, cparams,
                                 nullptr));
       p->launches += 1;
     }
@@ -322,7 +321,7 @@ int jacobi_solve(pml_plan* p, const pml_workspace* ws, const PmlArgs& tbl,
                              cudaMemcpyDeviceToHost, (cudaStream_t)s));
     PML_CUDA(cudaStreamSynchronize((cudaStream_t)s));
     if (host_flags[0]) break;
-    if (batch < 4096) batch *= 2;
+    if (batch < 8192) batch *= 2;
   }
   const long long sweeps = host_flags[1];
   if (sweeps_out) *sweeps_out = (int)sweeps;
@@ -541,10 +540,14 @@ int pml_plan_create(const char* source, const pml_plan_desc* desc,
     pml_plan_destroy(p);
     return fail("missing kernel pml_eval_rhs");
   }
+  // (cubins of older template versions may lack it: optional)
+  if (g_drv.moduleGetFunction(&p->apply_dir, p->module, "pml_apply_dirichlet_planes") !=
+      CUDA_SUCCESS)
+    p->apply_dir = nullptr;
   if (desc->n_lap > 0) {
     struct { const char* n; CUfunction* f; } js[] = {
         {"pml_jacobi_init", &p->jac_init}, {"pml_jacobi_sweep", &p->jac_sweep},
-        {"pml_jacobi_check", &p->jac_check}, {"pml_jacobi_store", &p->jac_store}};
+        {"pml_jacobi_store", &p->jac_store}};
     for (auto& j : js) {
       r = g_drv.moduleGetFunction(j.f, p->module, j.n);
       if (r != CUDA_SUCCESS) {
@@ -596,11 +599,47 @@ int pml_plan_set_tables(pml_plan* p, const pml_tables* t) {
 
 long long pml_plan_launches(const pml_plan* p) { return p ? p->launches : 0; }
 
+static int fdm_run_batch(pml_plan* p, int integrator, const pml_workspace* ws,
+                         const double* y0, double* traj, long long stride,
+                         int batch, long long y_batch_stride,
+                         long long traj_batch_stride, long long ws_batch_stride,
+                         const double* t_host, int n_steps, double d_t,
+                         long long slot0, const double* jacobi_init,
+                         double jacobi_tol, long long max_sweeps,
+                         int* sweeps_out, void* stream);
+
 int pml_fdm_run(pml_plan* p, int integrator, const pml_workspace* ws,
                 const double* y0, double* traj, long long stride,
                 const double* t_host, int n_steps, double d_t, long long slot0,
                 const double* jacobi_init, double jacobi_tol,
                 long long max_sweeps, int* sweeps_out, void* stream) {
+  return fdm_run_batch(p, integrator, ws, y0, traj, stride, 1, 0, 0, 0, t_host,
+                       n_steps, d_t, slot0, jacobi_init, jacobi_tol, max_sweeps,
+                       sweeps_out, stream);
+}
+
+int pml_fdm_run_batch(pml_plan* p, int integrator, const pml_workspace* ws,
+                      const double* y0, double* traj, long long stride,
+                      int batch, long long y_batch_stride,
+                      long long traj_batch_stride, long long ws_batch_stride,
+                      const double* t_host, int n_steps, double d_t,
+                      long long slot0, void* stream) {
+  if (batch < 1) return fail("empty batch");
+  if (p && p->desc.n_lap > 0)
+    return fail("batched solves of systems with Y_LAPLACIAN equations");
+  return fdm_run_batch(p, integrator, ws, y0, traj, stride, batch,
+                       y_batch_stride, traj_batch_stride, ws_batch_stride, t_host,
+                       n_steps, d_t, slot0, nullptr, 0.0, 0, nullptr, stream);
+}
+
+static int fdm_run_batch(pml_plan* p, int integrator, const pml_workspace* ws,
+                         const double* y0, double* traj, long long stride,
+                         int batch, long long y_batch_stride,
+                         long long traj_batch_stride, long long ws_batch_stride,
+                         const double* t_host, int n_steps, double d_t,
+                         long long slot0, const double* jacobi_init,
+                         double jacobi_tol, long long max_sweeps,
+                         int* sweeps_out, void* stream) {
   if (!p || !ws || !y0 || !traj || !t_host) return fail("null argument");
   if (integrator < 0 || integrator > 2) return fail("unknown integrator");
   if (p->desc.n_lap > 0 && !jacobi_init)
@@ -635,8 +674,11 @@ int pml_fdm_run(pml_plan* p, int integrator, const pml_workspace* ws,
       f.u_a = ws->u_a;
       f.u_b = ws->u_b;
       f.acc = ws->acc;
+      f.y_batch_stride = first == 0 ? y_batch_stride : traj_batch_stride;
+      f.traj_batch_stride = traj_batch_stride;
+      f.ws_batch_stride = ws_batch_stride;
       void* sparams[] = {&f};
-      PML_CU(g_drv.launchKernel(p->small_run, 1, 1, 1,
+      PML_CU(g_drv.launchKernel(p->small_run, (unsigned)batch, 1, 1,
                                 (unsigned)p->desc.small_threads, 1, 1, 0, s,
                                 sparams, nullptr));
       p->launches += 1;
@@ -644,6 +686,14 @@ int pml_fdm_run(pml_plan* p, int integrator, const pml_workspace* ws,
       PML_CUDA(cudaStreamSynchronize((cudaStream_t)s));
     }
     return 0;
+  }
+  // large meshes: every member saturates the device, members run in turn
+  // (they share the scratch buffers)
+  for (int b = 1; b < batch; ++b) {
+    if (fdm_run_batch(p, integrator, ws, y0 + b * y_batch_stride,
+                      traj + b * traj_batch_stride, stride, 1, 0, 0, 0, t_host,
+                      n_steps, d_t, slot0, nullptr, 0.0, 0, nullptr, stream))
+      return -1;
   }
   for (int j = 0; j < n_steps; ++j) {
     const double t = t_host[j];
@@ -707,6 +757,18 @@ int pml_eval_rhs(pml_plan* p, const double* u, double* out, double t,
   bind_dir(p, a.dir_full, slot);
   void* params[] = {&a};
   return launch(p, p->eval_rhs, params, (CUstream)stream);
+}
+
+int pml_apply_dirichlet(pml_plan* p, double* planes, long long slot, void* stream) {
+  if (!p || !planes) return fail("null argument");
+  if (!p->apply_dir) return fail("plan has no Dirichlet kernel");
+  PmlArgs a;
+  std::memset(&a, 0, sizeof(a));
+  fill_tables(p, a);
+  bind_dir(p, a.dir, slot);
+  a.u_out = planes;
+  void* params[] = {&a};
+  return launch(p, p->apply_dir, params, (CUstream)stream);
 }
 
 int pml_jacobi_run(pml_plan* p, const pml_workspace* ws, const double* rhs,
@@ -831,6 +893,111 @@ shift_kernel(double* __restrict__ traj, long long n_steps, long long stride,
   (void)n_steps;
 }
 
+struct IcMesh {
+  int n_dims;
+  int shape[3];
+  int coord;
+  const double* axis[3];
+  const double* trig[4];
+};
+struct IcGaussian {
+  pml_ic_gaussian_params comp[PML_IC_MAX_COMPONENTS];
+};
+struct IcFactors {
+  const double* f[PML_IC_MAX_COMPONENTS * 3];
+  double multiplier[PML_IC_MAX_COMPONENTS];
+};
+
+__device__ __forceinline__ void ic_cell(const IcMesh& m, long long cell, int& i0,
+                                        int& i1, int& i2) {
+  const int n1 = m.shape[1], n2 = m.shape[2];
+  i2 = (int)(cell % n2);
+  const long long r = cell / n2;
+  i1 = (int)(r % n1);
+  i0 = (int)(r / n1);
+}
+
+// Cartesian coordinates of a vertex, formed like mesh.py:to_cartesian_coordinates
+// (trigonometric factors evaluated by the host, products in the same order)
+__device__ __forceinline__ void ic_cartesian(const IcMesh& m, int i0, int i1,
+                                             int i2, double* x) {
+  const double a0 = __ldg(m.axis[0] + i0);
+  const double a1 = m.n_dims > 1 ? __ldg(m.axis[1] + i1) : 0.0;
+  const double a2 = m.n_dims > 2 ? __ldg(m.axis[2] + i2) : 0.0;
+  if (m.coord == 0) {
+    x[0] = a0;
+    x[1] = a1;
+    x[2] = a2;
+  } else if (m.coord == 3) {
+    const double ct = __ldg(m.trig[0] + i1), st = __ldg(m.trig[1] + i1);
+    const double sp = __ldg(m.trig[2] + i2), cp = __ldg(m.trig[3] + i2);
+    x[0] = a0 * sp * ct;
+    x[1] = a0 * sp * st;
+    x[2] = a0 * cp;
+  } else {
+    const double ct = __ldg(m.trig[0] + i1), st = __ldg(m.trig[1] + i1);
+    x[0] = a0 * ct;
+    x[1] = a0 * st;
+    x[2] = a2;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+ic_gaussian_kernel(const __grid_constant__ IcMesh m, int y_dim,
+                   const __grid_constant__ IcGaussian g, double* __restrict__ planes,
+                   long long n_cells) {
+  for (long long cell = blockIdx.x * (long long)kThreads + threadIdx.x;
+       cell < n_cells; cell += (long long)gridDim.x * kThreads) {
+    int i0, i1, i2;
+    ic_cell(m, cell, i0, i1, i2);
+    double x[3];
+    ic_cartesian(m, i0, i1, i2, x);
+    const int d = m.n_dims;
+    for (int c = 0; c < y_dim; ++c) {
+      const pml_ic_gaussian_params& p = g.comp[c];
+      double maha = 0.0;
+      for (int k = 0; k < d; ++k) {
+        double w = 0.0;
+        for (int j = 0; j < d; ++j) w += (x[j] - p.mean[j]) * p.whiten[j * d + k];
+        maha += w * w;
+      }
+      planes[(long long)c * n_cells + cell] =
+          exp(-0.5 * (p.log_norm + maha)) * p.multiplier;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+ic_separable_kernel(const __grid_constant__ IcMesh m, int y_dim,
+                    const __grid_constant__ IcFactors f, double* __restrict__ planes,
+                    long long n_cells) {
+  for (long long cell = blockIdx.x * (long long)kThreads + threadIdx.x;
+       cell < n_cells; cell += (long long)gridDim.x * kThreads) {
+    int i[3];
+    ic_cell(m, cell, i[0], i[1], i[2]);
+    for (int c = 0; c < y_dim; ++c) {
+      double v = __ldg(f.f[c * m.n_dims] + i[0]);
+      for (int a = 1; a < m.n_dims; ++a) v *= __ldg(f.f[c * m.n_dims + a] + i[a]);
+      planes[(long long)c * n_cells + cell] = v * f.multiplier[c];
+    }
+  }
+}
+
+int ic_mesh_from(const pml_ic_mesh* mesh, IcMesh& m, long long& n_cells) {
+  if (!mesh || mesh->n_dims < 1 || mesh->n_dims > 3)
+    return fail("initial conditions on the device need a mesh with 1..3 axes");
+  m.n_dims = mesh->n_dims;
+  m.coord = mesh->coord;
+  n_cells = 1;
+  for (int a = 0; a < 3; ++a) {
+    m.shape[a] = a < mesh->n_dims ? mesh->shape[a] : 1;
+    m.axis[a] = mesh->axis_dev[a];
+    n_cells *= m.shape[a];
+  }
+  for (int a = 0; a < 4; ++a) m.trig[a] = mesh->trig_dev[a];
+  return 0;
+}
+
 unsigned grid_for(long long n, unsigned cap = 148 * 16) {
   long long b = (n + kThreads - 1) / kThreads;
   if (b < 1) b = 1;
@@ -857,6 +1024,46 @@ int pml_soa_to_aos(const double* soa, double* aos, long long n_cells, int y_dim,
   if (total == 0) return 0;
   soa_to_aos_kernel<<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(
       soa, aos, n_cells, y_dim, total);
+  PML_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int pml_ic_gaussian(const pml_ic_mesh* mesh, int y_dim,
+                    const pml_ic_gaussian_params* params, double* planes,
+                    void* stream) {
+  if (!params || !planes) return fail("null argument");
+  if (y_dim < 1 || y_dim > PML_IC_MAX_COMPONENTS)
+    return fail("too many components for a device-side initial condition");
+  IcMesh m;
+  long long n_cells;
+  if (ic_mesh_from(mesh, m, n_cells)) return -1;
+  IcGaussian g;
+  std::memset(&g, 0, sizeof(g));
+  for (int c = 0; c < y_dim; ++c) g.comp[c] = params[c];
+  ic_gaussian_kernel<<<grid_for(n_cells), kThreads, 0, (cudaStream_t)stream>>>(
+      m, y_dim, g, planes, n_cells);
+  PML_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int pml_ic_separable(const pml_ic_mesh* mesh, int y_dim,
+                     const double* const* factors, const double* multipliers,
+                     double* planes, void* stream) {
+  if (!factors || !multipliers || !planes) return fail("null argument");
+  if (y_dim < 1 || y_dim > PML_IC_MAX_COMPONENTS)
+    return fail("too many components for a device-side initial condition");
+  IcMesh m;
+  long long n_cells;
+  if (ic_mesh_from(mesh, m, n_cells)) return -1;
+  if (m.coord != 0) return fail("separable initial conditions need a Cartesian mesh");
+  IcFactors f;
+  std::memset(&f, 0, sizeof(f));
+  for (int c = 0; c < y_dim; ++c) {
+    f.multiplier[c] = multipliers[c];
+    for (int a = 0; a < m.n_dims; ++a) f.f[c * m.n_dims + a] = factors[c * m.n_dims + a];
+  }
+  ic_separable_kernel<<<grid_for(n_cells), kThreads, 0, (cudaStream_t)stream>>>(
+      m, y_dim, f, planes, n_cells);
   PML_CUDA(cudaGetLastError());
   return 0;
 }

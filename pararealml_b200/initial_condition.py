@@ -11,10 +11,17 @@ from typing import Callable, Optional, Sequence, Tuple
 
 import numpy as np
 from scipy.interpolate import interpn
+from scipy.linalg import eigh as scipy_eigh
 from scipy.stats import beta, multivariate_normal
 
 from pararealml_b200.constraint import apply_constraints_along_last_axis
 from pararealml_b200.mesh import to_cartesian_coordinates
+
+def torch_empty(n: int, device):
+    import torch
+
+    return torch.empty(n, dtype=torch.float64, device=device)
+
 
 VectorizedInitialConditionFunction = Callable[
     [Optional[np.ndarray]], np.ndarray
@@ -134,19 +141,32 @@ class ContinuousInitialCondition(InitialCondition):
             self._multipliers = np.array(multipliers)
         self._cp = cp
         self._y_0_func = y_0_func
-        self._discrete = {
-            True: self._discretise(True),
-            False: self._discretise(False),
-        }
+        # discretised on first use (the reference does it in the constructor,
+        # initial_condition.py:212-229; the values are the same): a large mesh
+        # whose state is evaluated on the device never pays for the host arrays
+        self._discrete = {}
 
     def y_0(self, x):
         return np.multiply(self._y_0_func(x), self._multipliers)
 
+    def _discrete_y_0(self, vertex_oriented) -> np.ndarray:
+        key = bool(vertex_oriented)
+        if key not in self._discrete:
+            self._discrete[key] = self._discretise(key)
+        return self._discrete[key]
+
     def discrete_y_0_view(self, vertex_oriented=None):
-        return self._discrete[bool(vertex_oriented)]
+        return self._discrete_y_0(vertex_oriented)
 
     def discrete_y_0(self, vertex_oriented=None):
-        return np.copy(self._discrete[bool(vertex_oriented)])
+        return np.copy(self._discrete_y_0(vertex_oriented))
+
+    def discrete_y_0_planes(self, plan):
+        """Vertex-oriented initial state as component planes on the device of
+        ``plan`` (a ``DevicePlan`` of this problem, whose static Dirichlet
+        tables are applied), evaluated by a CUDA kernel -- or None when this
+        initial condition has no device form (arbitrary Python callables)."""
+        return None
 
     def _discretise(self, vertex_oriented: bool) -> np.ndarray:
         cp = self._cp
@@ -211,6 +231,42 @@ class GaussianInitialCondition(ContinuousInitialCondition):
             out[:, i] = multivariate_normal.pdf(xc, mean=mean, cov=cov)
         return out
 
+    def discrete_y_0_planes(self, plan):
+        """The densities evaluated by ``pml_ic_gaussian`` with SciPy's
+        formula: exp(-0.5 (rank log(2 pi) + log pdet(cov) + |(x - mean) U|^2))
+        where U = eigenvectors * sqrt(1 / eigenvalues) of the covariance."""
+        from pararealml_b200 import _native
+        from pararealml_b200.operators.fdm import device as dv
+
+        y_dim = len(self._means_and_covs)
+        if y_dim > _native.IC_MAX_COMPONENTS:
+            return None
+        d = self._cp.differential_equation.x_dimension
+        params = (_native.IcGaussianParams * y_dim)()
+        for c, (mean, cov) in enumerate(self._means_and_covs):
+            s, u = scipy_eigh(np.asarray(cov, dtype=float), lower=True)
+            eps = 1e6 * np.finfo(s.dtype).eps * np.max(np.abs(s))
+            if np.min(s) < -eps or np.any(np.abs(s) <= eps):
+                return None  # singular covariance: left to SciPy on the host
+            whiten = np.multiply(u, np.sqrt(1.0 / s))
+            for j in range(d):
+                params[c].mean[j] = float(mean[j])
+                for k in range(d):
+                    params[c].whiten[j * d + k] = float(whiten[j, k])
+            params[c].log_norm = float(d * np.log(2.0 * np.pi) + np.sum(np.log(s)))
+            params[c].multiplier = float(self._multipliers[c])
+        mesh, keep = dv.ic_mesh(self._cp.mesh, plan.device)
+        planes = torch_empty(y_dim * plan.n_cells, plan.device)
+        _native.check(
+            _native.lib().pml_ic_gaussian(
+                mesh, y_dim, params, planes.data_ptr(), dv.stream_ptr()
+            )
+        )
+        dv.count_launch()
+        plan.apply_static_dirichlet(planes)
+        del keep
+        return planes
+
 
 class MarginalBetaProductInitialCondition(ContinuousInitialCondition):
     """Each component is a product of per-axis Beta PDFs."""
@@ -247,6 +303,44 @@ class MarginalBetaProductInitialCondition(ContinuousInitialCondition):
             )
             cols.append(col)
         return np.concatenate(cols, axis=-1)
+
+    def discrete_y_0_planes(self, plan):
+        """Cartesian meshes: the 1-D Beta densities of every axis are
+        evaluated on the host (n values each, the same SciPy calls as
+        ``_pdf``) and multiplied on the device (``pml_ic_separable``) in the
+        order ``np.prod`` multiplies them -- bit-identical to the host
+        discretisation."""
+        import ctypes
+
+        from pararealml_b200 import _native
+        from pararealml_b200.mesh import CoordinateSystem
+        from pararealml_b200.operators.fdm import device as dv
+
+        mesh_obj = self._cp.mesh
+        y_dim = len(self._all_alphas_and_betas)
+        if (mesh_obj.coordinate_system_type != CoordinateSystem.CARTESIAN
+                or y_dim > _native.IC_MAX_COMPONENTS):
+            return None
+        d = mesh_obj.dimensions
+        axes = mesh_obj.vertex_axis_coordinates
+        keep, ptrs = [], (ctypes.c_void_p * (y_dim * d))()
+        for c, params in enumerate(self._all_alphas_and_betas):
+            for k, (a, b) in enumerate(params):
+                vec = dv.to_device(beta.pdf(axes[k], a, b), plan.device)
+                keep.append(vec)
+                ptrs[c * d + k] = vec.data_ptr()
+        mult = (ctypes.c_double * y_dim)(*[float(m) for m in self._multipliers])
+        mesh, keep_mesh = dv.ic_mesh(mesh_obj, plan.device)
+        planes = torch_empty(y_dim * plan.n_cells, plan.device)
+        _native.check(
+            _native.lib().pml_ic_separable(
+                mesh, y_dim, ptrs, mult, planes.data_ptr(), dv.stream_ptr()
+            )
+        )
+        dv.count_launch()
+        plan.apply_static_dirichlet(planes)
+        del keep, keep_mesh
+        return planes
 
 
 def vectorize_ic_function(

@@ -143,6 +143,12 @@ class FusedTile:
     smem_first: int  # dynamic shared memory of the stage 1+2 / midpoint kernels
     smem_pointwise: int  # ... of the stage 3+4 kernel (adds y and acc rings)
     min_blocks: int
+    #: 1 = every thread runs both stages, one __syncthreads per plane;
+    #: 2 = warp-specialised pipeline (loader / stage-A / stage-B warps)
+    variant: int = 1
+    #: ring depths of the warp-specialised variant: input planes, stage-A
+    #: result planes, stage-A increments
+    rings: Tuple[int, int, int] = (5, 8, 7)
 
 
 SMEM_PER_BLOCK_MAX = 227 * 1024
@@ -169,6 +175,11 @@ def default_fused(shape, y_dim, n_dt=None, passthrough=False) -> Optional[FusedT
     # (measured: Cahn-Hilliard 256^3 runs 1.8x faster unfused)
     if mode != "1" and n_dt != y_dim:
         return None
+    variant = int(os.environ.get("PML_FVARIANT", "2"))
+    if variant == 2:
+        ws = _warp_specialised_tile(shape, y_dim, n_dt, passthrough)
+        if ws is not None:
+            return ws
     if os.environ.get("PML_FTILE"):
         tx, ty = (int(v) for v in os.environ["PML_FTILE"].split(","))
     elif nd == 3:
@@ -240,6 +251,76 @@ def default_fused(shape, y_dim, n_dt=None, passthrough=False) -> Optional[FusedT
                         65536 // (96 * threads)))
     min_blocks = int(os.environ.get("PML_FMIN_BLOCKS", str(per_sm)))
     return FusedTile(tx, ty, zc, depth, threads, first, pointwise, min_blocks)
+
+
+def _warp_specialised_tile(shape, y_dim, n_dt, passthrough) -> Optional[FusedTile]:
+    """Geometry of the warp-specialised stage-pair kernels: rows of the
+    stage-A tile (tile + halo 1) are whole warps, so the tile is 32 k - 2
+    cells wide; one loader warp, one stage-A warp per 32 cells of every
+    stage-A row, one stage-B warp per 32 cells of every tile row; one thread
+    block per SM (3-D) with ring depths that fit its shared memory."""
+    nd = len(shape)
+    hy = 1 if nd == 3 else 0
+    n_ring = n_dt if passthrough else y_dim
+
+    def pad16(n):
+        return -(-n // 16) * 16
+
+    if os.environ.get("PML_FTILE"):
+        tx, ty = (int(v) for v in os.environ["PML_FTILE"].split(","))
+    elif nd == 3:
+        tx, ty = 30, 8
+    else:
+        tx, ty = 126, 1
+    if nd == 2:
+        ty = 1
+    # the tile is not wider than the mesh rounded up to whole warps
+    tx = min(tx, 32 * -(-(shape[-1] + 2) // 32) - 2)
+    tx = max(30, 32 * ((tx + 2) // 32) - 2)
+    if nd == 3:
+        ty = max(1, min(ty, shape[1]))
+    rings = tuple(
+        int(v) for v in os.environ.get("PML_FRINGS", "5,8,7").split(",")
+    )
+
+    def geometry(tx, ty, rings):
+        s_in, s_mid, s_k = rings
+        mw, mh = tx + 2, ty + 2 * hy
+        iw, ih = tx + 4, ty + 4 * hy
+        wpr = mw // 32
+        threads = 32 * (1 + wpr * mh + wpr * ty)
+        in_slot = n_ring * pad16(iw * ih)
+        mid_slot = n_ring * mw * mh
+        k_slot = n_dt * pad16(tx * ty)
+        first = 8 * (s_in * in_slot + s_mid * mid_slot + s_k * k_slot)
+        return threads, first, first
+
+    while True:
+        threads, first, pointwise = geometry(tx, ty, rings)
+        if (threads <= 1024 and tx + 4 <= 256
+                and max(first, pointwise) + 1024 <= SMEM_PER_BLOCK_MAX):
+            break
+        if nd == 3 and ty > 2:
+            ty -= 2 if ty > 4 else 1
+        elif tx > 30:
+            tx -= 32
+        else:
+            return None
+    tiles = -(-shape[-1] // tx) * (-(-shape[1] // ty) if nd == 3 else 1)
+    # resident blocks per SM: shared memory, threads, and >= 80 registers
+    per_sm = max(1, min(SMEM_PER_SM // (max(first, pointwise) + 1024),
+                        2048 // threads, 65536 // (80 * threads)))
+    if os.environ.get("PML_FZC"):
+        zc = int(os.environ["PML_FZC"])
+    else:
+        # the pipeline fills and drains once per chunk (~4 planes): long
+        # chunks, but enough thread blocks for ~6 waves
+        chunks = max(1, -(-(6 * N_SMS * per_sm) // tiles))
+        zc = min(128, max(32, -(-shape[0] // chunks)))
+    zc = max(1, min(zc, shape[0]))
+    min_blocks = int(os.environ.get("PML_FMIN_BLOCKS", str(per_sm)))
+    return FusedTile(tx, ty, zc, 1, threads, first, pointwise, min_blocks,
+                     variant=2, rings=rings)
 
 
 class _LeafBuilder:
@@ -581,13 +662,20 @@ def generate_source(spec: ProblemSpec) -> str:
         f"#define PML_NLAP {len(lap_idx)}",
         f"#define PML_STREAMING {int(os.environ.get('PML_STREAM', '0'))}",
         f"#define PML_MIN_BLOCKS {min_blocks}",
-        f"#define PML_FUSED {int(fused is not None)}",
+        f"#define PML_FUSED {fused.variant if fused else 0}",
         f"#define PML_FTX {fused.tx if fused else 32}",
         f"#define PML_FTY {fused.ty if fused else 1}",
         f"#define PML_FZC {fused.zc if fused else 1}",
         f"#define PML_FDEPTH {fused.depth if fused else 1}",
         f"#define PML_F_THREADS {fused.threads if fused else 32}",
         f"#define PML_FMIN_BLOCKS {fused.min_blocks if fused else 1}",
+        *(
+            f"#define PML_WS_{name} {value}"
+            for name, value in zip(
+                ("SIN", "SMID", "SK"),
+                fused.rings if (fused and fused.variant == 2) else (5, 8, 7),
+            )
+        ),
         f"#define PML_ZREP {max(1, int(spec.zrep))}",
         f"#define PML_JREP {JACOBI_REP}",
         f"#define PML_BX {block[0]}",

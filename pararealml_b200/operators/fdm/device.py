@@ -54,6 +54,43 @@ def cubin_path(source: str) -> str:
     return os.path.join(CACHE_DIR, codegen.source_key(source) + ".cubin")
 
 
+def count_launch(n: int = 1):
+    global _TOTAL_LAUNCHES
+    _TOTAL_LAUNCHES += n
+
+
+def to_device(array: np.ndarray, device) -> torch.Tensor:
+    return _from_numpy(np.asarray(array, dtype=np.float64)).to(device)
+
+
+def ic_mesh(mesh, device):
+    """``pml_ic_mesh`` of a mesh (axis coordinate vectors and, for curvilinear
+    meshes, the host-evaluated trigonometric factors of
+    ``mesh.py:to_cartesian_coordinates``) plus the tensors it points at."""
+    from pararealml_b200.operators.fdm.codegen import COORD_CODES
+
+    out = _native.IcMesh()
+    axes = mesh.vertex_axis_coordinates
+    out.n_dims = len(axes)
+    out.coord = COORD_CODES[mesh.coordinate_system_type.name]
+    keep = []
+    for a in range(3):
+        out.shape[a] = len(axes[a]) if a < len(axes) else 1
+        if a < len(axes):
+            t = to_device(axes[a], device)
+            keep.append(t)
+            out.axis_dev[a] = t.data_ptr()
+    if out.coord != 0:
+        trig = [np.cos(axes[1]), np.sin(axes[1])]
+        if out.coord == 3:
+            trig += [np.sin(axes[2]), np.cos(axes[2])]
+        for i, v in enumerate(trig):
+            t = to_device(v, device)
+            keep.append(t)
+            out.trig_dev[i] = t.data_ptr()
+    return ctypes.byref(out), (out, keep)
+
+
 def total_launches() -> int:
     """Kernels launched by this process through plans (bench accounting)."""
     return _TOTAL_LAUNCHES + sum(p.launches for p in _PLANS.values())
@@ -77,7 +114,7 @@ class DevicePlan:
             desc.shape[i] = shape3[i]
             desc.block[i] = block[i]
         fused = spec.fused
-        desc.fused = int(fused is not None)
+        desc.fused = fused.variant if fused is not None else 0
         if fused is not None:
             desc.fused_tile[0], desc.fused_tile[1] = fused.tx, fused.ty
             desc.fused_zc = fused.zc
@@ -135,7 +172,7 @@ class DevicePlan:
                 "u_b": torch.empty(n, **f64),
                 "acc": torch.empty(n, **f64),
                 "partials": torch.empty(max(self.n_blocks, 1), **f64),
-                "flags": torch.zeros(2, dtype=torch.int32, device=self.device),
+                "flags": torch.zeros(4, dtype=torch.int32, device=self.device),
             }
             nl = max(self.n_lap, 0) * self.n_cells
             for k in ("lap_rhs", "jac_a", "jac_b"):
@@ -239,6 +276,64 @@ class DevicePlan:
             )
         )
         return np.array(sweeps[:n_steps]) if self.n_lap else None
+
+    def run_batch(
+        self,
+        integrator: str,
+        y0: torch.Tensor,
+        traj: torch.Tensor,
+        t_starts: np.ndarray,
+        d_t: float,
+        slot0: int = 0,
+    ):
+        """``len(t_starts)`` steps of every member of a batch: ``y0`` is
+        (batch, y_dim * n_cells) planes, ``traj`` (batch, steps, y_dim *
+        n_cells).  Small meshes: one launch, one thread block per member."""
+        batch, n_steps = y0.shape[0], len(t_starts)
+        assert traj.shape[0] == batch and traj.shape[1] >= n_steps
+        assert y0.is_contiguous() and traj.is_contiguous()
+        ws = self.workspace()
+        keep = None
+        ws_stride = 0
+        if self.spec.small_threads and batch > 1:
+            # every member needs its own stage buffers
+            n = self.n_cells * self.y_dim
+            keep = torch.empty((3, batch, n), dtype=torch.float64, device=self.device)
+            batched = _native.Workspace()
+            ctypes.memmove(
+                ctypes.byref(batched), ctypes.byref(ws), ctypes.sizeof(ws)
+            )
+            batched.u_a, batched.u_b, batched.acc = (
+                keep[0].data_ptr(), keep[1].data_ptr(), keep[2].data_ptr()
+            )
+            ws, ws_stride = batched, n
+        t_host = np.ascontiguousarray(t_starts, dtype=np.float64)
+        _native.check(
+            _native.lib().pml_fdm_run_batch(
+                self.handle, _native.INTEGRATOR_CODES[integrator],
+                ctypes.byref(ws), y0.data_ptr(), traj.data_ptr(),
+                traj.stride(1), batch, y0.stride(0), traj.stride(0), ws_stride,
+                t_host.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                n_steps, float(d_t), slot0, stream_ptr(),
+            )
+        )
+        if keep is not None:
+            keep.record_stream(torch.cuda.current_stream())
+
+    def apply_static_dirichlet(self, planes: torch.Tensor):
+        """Writes the static Dirichlet values of the problem into component
+        planes (what ``DiscreteInitialCondition`` does on the host,
+        initial_condition.py:86-89)."""
+        if self.low.dir_mask == 0:
+            return
+        if not self.low.all_static:
+            raise ValueError("static Dirichlet values of a dynamic problem")
+        self.bind_tables(self.low)
+        _native.check(
+            _native.lib().pml_apply_dirichlet(
+                self.handle, planes.data_ptr(), 0, stream_ptr()
+            )
+        )
 
     def eval_rhs(self, u: torch.Tensor, out: torch.Tensor, t: float = 0.0):
         _native.check(

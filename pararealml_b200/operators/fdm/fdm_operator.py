@@ -39,6 +39,9 @@ TRAJECTORY_CHUNK_BYTES = int(
 )
 # time steps per upload of dynamic boundary tables
 DYNAMIC_BC_CHUNK_STEPS = 256
+# meshes of at least this many vertices evaluate initial conditions that have
+# a device form (Gaussian, marginal Beta product) on the GPU
+DEVICE_IC_MIN_CELLS = int(os.environ.get("PML_DEVICE_IC_MIN_CELLS", str(1 << 18)))
 
 
 def lowered(cp) -> LoweredProblem:
@@ -54,8 +57,25 @@ def lowered(cp) -> LoweredProblem:
     return low
 
 
-def plan_overrides(cp, low: LoweredProblem, y0: Optional[np.ndarray]) -> dict:
-    """Code generation switches of the stage kernels for this problem."""
+def has_device_initial_condition(ic, low: LoweredProblem) -> bool:
+    """True if the initial state can be evaluated on the device
+    (``discrete_y_0_planes``) and the mesh is large enough for that to pay."""
+    from pararealml_b200.initial_condition import ContinuousInitialCondition
+
+    method = getattr(type(ic), "discrete_y_0_planes", None)
+    return bool(
+        method is not None
+        and method is not ContinuousInitialCondition.discrete_y_0_planes
+        and low.n_dims and low.all_static
+        and low.n_cells >= DEVICE_IC_MIN_CELLS
+    )
+
+
+def plan_overrides(cp, low: LoweredProblem, y0: Optional[np.ndarray],
+                   dirichlet_satisfied: bool = False) -> dict:
+    """Code generation switches of the stage kernels for this problem.
+    ``dirichlet_satisfied``: the initial state carries the static Dirichlet
+    values by construction (device-side initial conditions)."""
     for sym in set().union(*[e.free_symbols for e in low.rhs]):
         if sym.name.startswith("y-vector-laplacian"):
             # the reference's symbol mapper never stores this evaluator
@@ -66,7 +86,7 @@ def plan_overrides(cp, low: LoweredProblem, y0: Optional[np.ndarray]) -> dict:
     if n_other and low.all_static and low.n_dims:
         # the stage inputs of the non-dt components equal y itself when y
         # already satisfies the (static) Dirichlet values
-        if low.dir_mask == 0:
+        if low.dir_mask == 0 or dirichlet_satisfied:
             passthrough = True
         elif y0 is not None:
             probe = apply_dirichlet_host(cp, np.array(y0, copy=True), None)
@@ -140,9 +160,13 @@ class FDMOperator(Operator):
         y0_planes: torch.Tensor,
         t: np.ndarray,
         traj: torch.Tensor,
+        jacobi_starts: Optional[torch.Tensor] = None,
     ):
         """Advances ``y0_planes`` (component planes) through the steps
-        starting at ``t[:-1]`` and writes step j to ``traj[j]``."""
+        starting at ``t[:-1]`` and writes step j to ``traj[j]``.
+        ``jacobi_starts`` (systems with Y_LAPLACIAN equations, static boundary
+        conditions): start values already drawn with ``_draw_jacobi_starts``
+        and resident on the device, one per step."""
         low = plan.low
         n_steps = len(t) - 1
         d_t = self._d_t
@@ -150,7 +174,9 @@ class FDMOperator(Operator):
         sweeps_log = []
         if low.all_static or low.n_dims == 0:
             plan.bind_tables(low)
-            jac = self._draw_jacobi_starts(plan, n_steps)
+            jac = jacobi_starts
+            if jac is None:
+                jac = self._draw_jacobi_starts(plan, n_steps)
             s = plan.run(
                 self._family, y0_planes, traj, t[:-1], d_t, 0, jac, tol,
                 self.max_jacobi_sweeps,
@@ -200,6 +226,11 @@ class FDMOperator(Operator):
         t = discretize_time_domain(ivp.t_interval, self._d_t)
         low = lowered(cp)
         ic = ivp.initial_condition
+        if has_device_initial_condition(ic, low):
+            # the state at t0 is evaluated on the device (``initial_planes``);
+            # no host array of it is ever formed
+            plan = dv.get_plan(low, **plan_overrides(cp, low, None, True))
+            return cp, t, None, low, plan
         dynamic = bool(low.n_dims and not low.all_static)
         view = getattr(ic, "discrete_y_0_view", None)
         y0 = None if (dynamic or view is None) else view(True)
@@ -210,12 +241,25 @@ class FDMOperator(Operator):
         plan = self._plan_for(cp, low, y0)
         return cp, t, y0, low, plan
 
+    @staticmethod
+    def initial_planes(ivp, low: LoweredProblem, plan, y0: Optional[np.ndarray]):
+        """The state at t0 as component planes on the device: uploaded from
+        the host array ``y0`` of ``prepare``, or -- ``y0`` None -- evaluated
+        by the initial condition's CUDA kernel."""
+        if y0 is None:
+            ic = ivp.initial_condition
+            planes = ic.discrete_y_0_planes(plan)
+            if planes is not None:
+                return planes
+            y0 = ic.discrete_y_0(True)  # no device form after all
+        return dv.upload_state(y0, low.n_cells, low.y_dim)
+
     def solve_on_device(self, ivp, y0_planes: Optional[torch.Tensor] = None):
         """Solves with the whole trajectory kept in HBM.  Returns
         ``(t[1:], trajectory planes (n_steps, y_dim * n_cells))``."""
         cp, t, y0, low, plan = self.prepare(ivp)
         if y0_planes is None:
-            y0_planes = dv.upload_state(y0, low.n_cells, low.y_dim)
+            y0_planes = self.initial_planes(ivp, low, plan, y0)
         traj = torch.empty(
             (len(t) - 1, low.y_dim * low.n_cells),
             dtype=torch.float64, device=plan.device,
@@ -278,6 +322,62 @@ class FDMOperator(Operator):
             ivp, t[1:], y, vertex_oriented=True, d_t=self._d_t, copy=False
         )
 
+    def solve_batch(self, ivps, parallel_enabled: bool = True):
+        """Solves several IVPs of ONE constrained problem over ONE time
+        interval that differ only in their initial conditions -- what the
+        data generation of the reference's ``SupervisedMLOperator`` does with
+        its oracle operator (supervised_ml_operator.py:130-236, one
+        ``solve`` per perturbed sub-IVP, fanned out over host processes) --
+        as one batched device run: small meshes
+        integrate all members in a single launch, one thread block per member.
+        Returns the list of ``Solution`` objects, each bit-identical to
+        ``solve(ivp)``.  IVPs that cannot be batched are solved one by one."""
+        ivps = list(ivps)
+        if not ivps:
+            return []
+        first = ivps[0]
+        cp = first.constrained_problem
+        low = lowered(cp)
+        batchable = (
+            len(ivps) > 1
+            and not self.spatial_decomposition
+            and all(v.constrained_problem is cp for v in ivps)
+            and all(tuple(v.t_interval) == tuple(first.t_interval) for v in ivps)
+            and not low.kind_indices("Y_LAPLACIAN")
+            and (low.all_static or low.n_dims == 0)
+        )
+        if not batchable:
+            return [self.solve(v, parallel_enabled) for v in ivps]
+        t = discretize_time_domain(first.t_interval, self._d_t)
+        n_steps, batch = len(t) - 1, len(ivps)
+        state = low.y_dim * low.n_cells
+        y0s = np.stack([v.initial_condition.discrete_y_0(True) for v in ivps])
+        # one plan for the batch: a component that is not time-stepped may
+        # only be passed through if every member satisfies the Dirichlet values
+        plans = {id(self._plan_for(cp, low, y0)): self._plan_for(cp, low, y0)
+                 for y0 in y0s}
+        if len(plans) > 1:
+            return [self.solve(v, parallel_enabled) for v in ivps]
+        plan = next(iter(plans.values()))
+        dev = dv.require_cuda()
+        flat = dv._from_numpy(y0s.reshape(-1))
+        y_dev = dv.aos_to_soa(
+            dv._to_device_staged(flat, dev), low.n_cells, low.y_dim, batch
+        ).view(batch, state)
+        traj = torch.empty((batch, n_steps, state), dtype=torch.float64, device=dev)
+        plan.bind_tables(low)
+        plan.run_batch(self._family, y_dev, traj, t[:-1], self._d_t)
+        host = torch.empty((batch, n_steps, state), dtype=torch.float64, pin_memory=True)
+        aos = dv.soa_to_aos(traj.view(-1), low.n_cells, low.y_dim, batch * n_steps)
+        host.view(-1).copy_(aos, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        y_shape = tuple(cp.y_vertices_shape)
+        ys = host.numpy().reshape((batch, n_steps) + y_shape)
+        return [
+            Solution(v, t[1:], ys[b], vertex_oriented=True, d_t=self._d_t, copy=False)
+            for b, v in enumerate(ivps)
+        ]
+
     def solve(self, ivp, parallel_enabled: bool = True) -> Solution:
         if self.spatial_decomposition:
             return self._solve_decomposed(ivp)
@@ -290,7 +390,7 @@ class FDMOperator(Operator):
         host = torch.empty(
             (n_steps, state), dtype=torch.float64, pin_memory=True
         )
-        y_prev = dv.upload_state(y0, low.n_cells, low.y_dim)
+        y_prev = self.initial_planes(ivp, low, plan, y0)
 
         chunk = max(1, min(n_steps, TRAJECTORY_CHUNK_BYTES // (state * 8)))
         if state * 8 >= (64 << 20) and n_steps >= 2:

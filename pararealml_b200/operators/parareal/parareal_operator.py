@@ -88,6 +88,12 @@ class _World:
         else:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
 
+    def all_reduce_max_async(self, t: torch.Tensor) -> "_PendingMax":
+        """Starts the max-reduction of ``t`` (device tensor on the current
+        stream) and returns a handle whose host value can be polled: the
+        current stream does not wait for the collective."""
+        return _PendingMax(self, t)
+
     def all_gather(self, t: torch.Tensor) -> torch.Tensor:
         """Every rank's ``t`` stacked along a new first axis."""
         if not self.active:
@@ -98,6 +104,59 @@ class _World:
         )
         dist.all_gather_into_tensor(out.view(-1), src.contiguous().view(-1))
         return out.to(t.device) if self._staged(t) else out
+
+
+class _PendingMax:
+    """An all-reduce(MAX) in flight.  NCCL: the collective runs on the
+    communicator's stream and the result is copied to pinned host memory on a
+    side stream, so kernels launched on the compute stream afterwards do not
+    wait for the slowest rank.  gloo (tests): the staged host tensor."""
+
+    _side = {}
+
+    def __init__(self, world: "_World", t: torch.Tensor):
+        self._event = None
+        self._work = None
+        if not world.active:
+            self._host = t.detach().cpu()
+            return
+        if world.on_gpu:
+            main = torch.cuda.current_stream()
+            key = t.device.index
+            side = _PendingMax._side.get(key)
+            if side is None:
+                side = _PendingMax._side[key] = torch.cuda.Stream(t.device)
+            self._buf = t
+            self._host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ready)
+                work = dist.all_reduce(t, op=dist.ReduceOp.MAX, async_op=True)
+                work.wait()  # orders the side stream after the collective
+                self._host.copy_(t, non_blocking=True)
+                self._event = torch.cuda.Event()
+                self._event.record(side)
+            t.record_stream(side)
+        else:
+            self._host = t.detach().cpu()
+            self._work = dist.all_reduce(
+                self._host, op=dist.ReduceOp.MAX, async_op=True
+            )
+
+    def ready(self) -> bool:
+        if self._event is not None:
+            return self._event.query()
+        if self._work is not None:
+            return self._work.is_completed()
+        return True
+
+    def result(self) -> np.ndarray:
+        if self._event is not None:
+            self._event.synchronize()
+        if self._work is not None:
+            self._work.wait()
+        return self._host.numpy()
 
 
 def _tolerances(condition, y_dim: int) -> np.ndarray:
@@ -130,6 +189,14 @@ class PararealOperator(Operator):
         self._termination_condition = termination_condition
         self._max_iterations = max_iterations
         self._gather_trajectory = gather_trajectory
+        #: device path: a rank starts the fine solve of the next iteration as
+        #: soon as it has passed its end point on, instead of idling until the
+        #: coarse chain has reached the last rank and the convergence test has
+        #: come back; the solve is dropped when the test says stop (costs a
+        #: second slice trajectory in HBM)
+        self.speculative_fine_solves = True
+        #: fine steps launched speculatively and then dropped (last solve)
+        self.last_wasted_fine_steps = 0
         #: corrective iterations executed by the most recent solve
         self.last_iterations = 0
         #: device planes of this rank's fine slice after the last solve
@@ -321,17 +388,25 @@ class PararealOperator(Operator):
         # initial state with the static Dirichlet values re-applied, as the
         # DiscreteInitialCondition of every sub-IVP does (reference :159-161)
         # (a caller-provided ``y0_planes`` must already satisfy them)
+        from pararealml_b200.operators.fdm import fdm_operator as fo
+
         y0 = None
-        if y0_planes is None:
-            ic = ivp.initial_condition
+        ic = ivp.initial_condition
+        on_device = y0_planes is None and fo.has_device_initial_condition(ic, low)
+        if y0_planes is None and not on_device:
             view = getattr(ic, "discrete_y_0_view", None)
             y0 = view(True) if view is not None else None
             if y0 is None:
                 y0 = ic.discrete_y_0(True)
             if low.dir_mask != 0:
                 y0 = DiscreteInitialCondition(cp, y0, True).discrete_y_0(True)
-        f_plan = f._plan_for(cp, low, y0)
-        g_plan = g._plan_for(cp, low, y0)
+        if on_device:
+            overrides = fo.plan_overrides(cp, low, None, True)
+            f_plan = g_plan = dv.get_plan(low, **overrides)
+            y0_planes = fo.FDMOperator.initial_planes(ivp, low, f_plan, None)
+        else:
+            f_plan = f._plan_for(cp, low, y0)
+            g_plan = g._plan_for(cp, low, y0)
 
         # one full-interval coarse solve on every rank (reference :133-139),
         # run slice by slice so that only one slice of it is resident
@@ -364,7 +439,8 @@ class PararealOperator(Operator):
         # sub-IVPs of the reference)
         t_f = discretize_time_domain((borders[rank], borders[rank + 1]), f.d_t)
         t_gs = discretize_time_domain((borders[rank], borders[rank + 1]), g.d_t)
-        fine = torch.empty((len(t_f) - 1, state), **f64)
+        n_fine = len(t_f) - 1
+        fines = [torch.empty((n_fine, state), **f64), None]
         g_slice = torch.empty((len(t_gs) - 1, state), **f64)
         corr = torch.empty(state, **f64)
         new_end = torch.empty(state, **f64)
@@ -372,15 +448,36 @@ class PararealOperator(Operator):
         scratch = torch.empty(y_dim * 1024, **f64)
         tol = _tolerances(self._termination_condition, y_dim)
         stream = dv.stream_ptr
+        max_it = min(size, self._max_iterations)
+        # speculation needs per-step launches (not the single-block time loop
+        # of small meshes) and room for a second slice trajectory
+        speculate = bool(
+            self.speculative_fine_solves and world.active and size > 1
+            and max_it > 1 and not f_plan.spec.small_threads
+        )
+        starts = [u_start, None]  # ping-pong: the start of the running fine
+        cur_s = 0                 # solve must survive the next hand-off
+        cur_f = 0                 # fines[cur_f]: fine solve of this iteration
+        launched = 0              # its steps already launched (speculatively)
 
-        have_fine = False
+        def fine_steps(src, dst, first, last):
+            """fine steps [first, last) of the slice that starts at ``src``"""
+            if last <= first:
+                return
+            prev = src if first == 0 else dst[first - 1]
+            f.integrate_on_device(
+                cp, f_plan, prev, t_f[first : last + 1], dst[first:last]
+            )
+
         self.last_iterations = 0
         self.last_update_norms = []
-        for i in range(min(size, self._max_iterations)):
+        self.last_wasted_fine_steps = 0
+        for i in range(max_it):
             self.last_iterations += 1
-            if not have_fine or rank >= i:
-                f.integrate_on_device(cp, f_plan, u_start, t_f, fine)
-                have_fine = True
+            if i == 0 or rank >= i:
+                fine_steps(starts[cur_s], fines[cur_f], launched, n_fine)
+            launched = 0
+            fine = fines[cur_f]
             _native.check(
                 lib.pml_parareal_correction(
                     fine[-1].data_ptr(), g_end.data_ptr(), corr.data_ptr(),
@@ -388,10 +485,17 @@ class PararealOperator(Operator):
                 )
             )
             sumsq.zero_()
+            next_s = cur_s
             if rank >= i:
                 if rank > i:
-                    world.recv(u_start, rank - 1)
-                    g.integrate_on_device(cp, g_plan, u_start, t_gs, g_slice)
+                    # the new slice start goes to the other buffer: the fine
+                    # solve reading the current one may still be running on a
+                    # rank that speculates
+                    next_s = 1 - cur_s
+                    if starts[next_s] is None:
+                        starts[next_s] = torch.empty(state, **f64)
+                    world.recv(starts[next_s], rank - 1)
+                    g.integrate_on_device(cp, g_plan, starts[next_s], t_gs, g_slice)
                     # the coarse end point is read in place (the slice buffer
                     # is only rewritten by the next coarse solve, after the
                     # next correction has been formed)
@@ -407,11 +511,44 @@ class PararealOperator(Operator):
                 if rank + 1 < size:
                     world.send(u_end, rank + 1)
             worst = torch.sqrt(sumsq / n_cells)
-            world.all_reduce_max(worst)
-            worst_host = worst.cpu().numpy()
-            self.last_update_norms.append(worst_host.copy())
+            if i + 1 >= max_it or not speculate:
+                world.all_reduce_max(worst)
+                worst_host = worst.cpu().numpy()
+            else:
+                # the test's answer arrives once the coarse chain has reached
+                # the last rank; until then this rank already steps through
+                # the fine solve of the next iteration (ranks > i: slice i is
+                # exact from now on), a few steps ahead of the device
+                pending = world.all_reduce_max_async(worst)
+                if rank > i:
+                    if fines[1 - cur_f] is None:
+                        try:
+                            fines[1 - cur_f] = torch.empty((n_fine, state), **f64)
+                        except torch.OutOfMemoryError:
+                            speculate = False
+                    in_flight = []
+                    while speculate and launched < n_fine and not pending.ready():
+                        if len(in_flight) >= 2:
+                            in_flight.pop(0).synchronize()
+                            if pending.ready():
+                                break
+                        fine_steps(starts[next_s], fines[1 - cur_f], launched, launched + 1)
+                        launched += 1
+                        mark = torch.cuda.Event()
+                        mark.record()
+                        in_flight.append(mark)
+                worst_host = pending.result()
+            self.last_update_norms.append(np.array(worst_host, copy=True))
             if bool(np.all(worst_host < tol)):
+                self.last_wasted_fine_steps = launched
                 break
+            if rank > i:
+                cur_s = next_s
+                if fines[1 - cur_f] is not None and launched > 0:
+                    cur_f = 1 - cur_f
+        fine = fines[cur_f]
+        if fines[1 - cur_f] is not None:
+            fines[1 - cur_f] = None  # the dropped / superseded trajectory
 
         shift_tmp = torch.empty(state, **f64)
         _native.check(

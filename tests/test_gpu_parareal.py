@@ -10,7 +10,7 @@ from dist_util import run_distributed
 pytestmark = pytest.mark.gpu
 
 
-def _solve(case_name, world_size, gather=True):
+def _solve(case_name, world_size, gather=True, speculative=True):
     import pararealml_b200 as ns
     from golden import cases
     from pararealml_b200.operators.fdm import (
@@ -27,6 +27,7 @@ def _solve(case_name, world_size, gather=True):
     f = FDMOperator(kinds[case.f[0]](), ThreePointCentralDifferenceMethod(), case.f[1])
     g = FDMOperator(kinds[case.g[0]](), ThreePointCentralDifferenceMethod(), case.g[1])
     p = PararealOperator(f, g, case.tol, gather_trajectory=gather)
+    p.speculative_fine_solves = speculative
     return case, p, p.solve(ivp)
 
 
@@ -68,6 +69,32 @@ def test_device_parareal_single_rank(case_name):
 @pytest.mark.parametrize("case_name", CASES[1:])
 def test_device_parareal_multi_rank_on_one_gpu(case_name, world_size):
     run_distributed(_worker, world_size, (case_name,))
+
+
+def _speculative_worker(rank, world_size, case_name):
+    """Multi-block kernels (no single-block time loop): the ranks launch the
+    next iteration's fine solve step by step while the convergence test is in
+    flight, and drop it when the test says stop."""
+    import os
+
+    import torch
+
+    os.environ["PML_SMALL"] = "0"
+    torch.cuda.set_device(0)
+    case, p, sol = _solve(case_name, world_size)
+    _check(case, p, sol, world_size)
+    # the same solve without speculation: bit-identical trajectory
+    _, q, sol_q = _solve(case_name, world_size, speculative=False)
+    assert np.array_equal(sol.discrete_y(), sol_q.discrete_y())
+    assert q.last_iterations == p.last_iterations
+
+
+@pytest.mark.parametrize("world_size", [2, 4])
+@pytest.mark.parametrize(
+    "case_name", ["parareal_diffusion_2d_multi_iteration", "parareal_burgers_3d"]
+)
+def test_device_parareal_speculative_fine_solves(case_name, world_size):
+    run_distributed(_speculative_worker, world_size, (case_name,))
 
 
 def _nccl_worker(rank, world_size, case_name):
