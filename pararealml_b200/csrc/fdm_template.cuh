@@ -25,6 +25,7 @@
 // Prelude contract (all compile-time):
 //   PML_NDIM, PML_C, PML_N0, PML_N1, PML_N2, PML_COORD (0 cart, 1 polar,
 //   2 cylindrical, 3 spherical), PML_NEU_MASK / PML_DIR_MASK (bit axis*2+side),
+//   PML_NEU_ZERO_MASK (faces whose Neumann table is 0.0 everywhere),
 //   PML_H0..2, PML_INV2H0..2, PML_INVHH0..2 (spacing constants),
 //   PML_NDT / PML_NALG / PML_NLAP and the index lists PML_DT_IDX, PML_ALG_IDX,
 //   PML_LAP_IDX, PML_KIND[c] (0 dt, 1 algebraic, 2 laplacian),
@@ -117,6 +118,8 @@ __device__ __forceinline__ double pml_neu(const PmlArgs& a, int comp, int i0,
                                           int i1, int i2) {
   constexpr int f = A * 2 + SIDE;
   if (!((PML_NEU_MASK >> f) & 1)) return PML_NAN;
+  // a static zero-flux face: the value is known at compile time
+  if ((PML_NEU_ZERO_MASK >> f) & 1) return 0.0;
   return __ldg(a.neu[f] + pml_face<A>(i0, i1, i2) * PML_C + comp);
 }
 
@@ -660,6 +663,9 @@ __device__ __forceinline__ void pml_mbar_wait(unsigned addr, unsigned parity) {
         : "memory");
   } while (!ok);
 }
+__device__ __forceinline__ void pml_mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 // one box (rows x columns of one component plane) global -> shared through the
 // TMA unit; cells outside the array arrive as zeros; completion (box bytes) is
 // signalled on the mbarrier
@@ -1026,394 +1032,574 @@ PML_FUSED_KERNEL(pml_fused_mid, PML_F_MID)
 #endif  // PML_FUSED
 
 // ---------------------------------------------------------------------------
-// Fused stage pairs, warp-specialised (PML_FUSED == 2): the same temporal
-// blocking as above, organised as a three-role pipeline inside one thread
-// block, coupled only by mbarriers (no __syncthreads in the plane loop):
+// Fused stage pairs, column-marching variant (PML_FUSED == 2): the same
+// temporal blocking and the same TMA / mbarrier plane rings as above, but the
+// arithmetic is organised around registers instead of shared memory:
 //
-//   loader warp   one lane issues the TMA boxes of every plane of stage A's
-//                 stencil input into a shared-memory ring, as soon as the
-//                 consumers have released the slot (the pointwise operands --
-//                 step-start value, accumulator -- are plain coalesced loads
-//                 of the compute warps, issued ahead of their barrier waits);
-//   A warps       one warp per 32 cells of a row of the stage-A tile (tile +
-//                 halo 1): stage A on plane p from the input ring, result to
-//                 the "mid" ring, its increment K to the "k" ring;
-//   B warps       one warp per 32 cells of a row of the tile: stage B on plane
-//                 p from the mid ring (needs planes p-1..p+1 of stage A),
-//                 outputs straight to HBM.
+//   * a thread owns PML_FROWS consecutive rows (axis 1) of one column of the
+//     stage-A tile and marches along axis 0.  The three planes z-1, z, z+1 of
+//     its own cells are held in registers for BOTH stages: stage A's input
+//     column is refilled with one shared-memory load per cell and plane, and
+//     stage B's input column is stage A's own result, which never has to be
+//     read back.  What is left for shared memory are the in-plane neighbours:
+//     a 7-point stencil costs (3 R + 2) / R loads per component in stage A and
+//     (2 R + 2) / R in stage B (R = rows per thread) instead of 7;
+//   * the plane loop is unrolled three times, so the register columns rotate
+//     by renaming, never by moves; all ring addresses, predicates and
+//     boundary-variant choices are loop invariants or per-iteration scalars
+//     instead of per-cell work;
+//   * warps whose cells are all interior run a branch-free body for all of
+//     their rows at once (independent cells interleave in the fp64 pipe);
+//     only the stores are predicated.
 //
-// Both compute roles march along axis 0 and keep the three values of their own
-// cell column (planes p-1, p, p+1) in registers, so a 7-point stencil costs 5
-// shared-memory loads per component instead of 7.  Every role runs at its own
-// pace: the A warps may lead the B warps by PML_WS_SMID - 2 planes, the loader
-// the A warps by the depth of the input ring.  Plane bookkeeping is in "steps"
-// r = plane - (zb - 2) of the chunk [zb, ze): the loader handles r = 0 ..
-// nB + 3, stage A r = 1 .. nB + 2, stage B r = 2 .. nB + 1; planes outside the
-// mesh are no-ops that still signal, so barrier slot r & 7 is in phase r >> 3
-// for every role.
-//   full[r & 7]   TMA bytes of loader step r (input plane r) have landed
-//   adone[r & 7]  every A warp has finished plane r
-//   bdone[r & 7]  every B warp has finished plane r
+// Iteration i (one __syncthreads() each): stage B on plane i - 1, stage A on
+// plane i + 1 -- exactly the schedule of the variant above, and per cell the
+// same sequence of arithmetic operations.
 // ---------------------------------------------------------------------------
 #if PML_FUSED == 2
-#define PML_WPR (PML_MW / 32)            // warps per row of the stage-A tile
-#define PML_NAW (PML_WPR * PML_MH)       // stage-A warps
-#define PML_NBW (PML_WPR * PML_FTY)      // stage-B warps
-#define PML_WS_THREADS (32 * (1 + PML_NAW + PML_NBW))
+#define PML_WPR (PML_MW / 32)                 // warps per row of the stage-A tile
+#define PML_R (PML_FHY ? PML_FROWS : 1)       // rows per thread
+#define PML_NRG (PML_MH / PML_R)              // row groups
 static_assert(PML_MW % 32 == 0, "stage-A tile rows are whole warps");
-static_assert(PML_WS_THREADS == PML_F_THREADS, "thread count of the plan");
+static_assert(PML_MH % PML_R == 0, "row groups tile the stage-A tile");
+static_assert(PML_F_THREADS == 32 * PML_WPR * PML_NRG, "thread count of the plan");
 
-// stencil source of a marching warp: the cell's own column (planes p-1, p,
-// p+1) is in registers, everything else is read from the ring
-template <int PITCH, int PLANE>
-struct PmlMarchSrc {
-  const double* base[3];
-  const double* y;  // passthrough components are read from the state itself
-  double v[PML_NRING][3];
+// stencil source of a marching thread: its own cells (PML_R rows, planes
+// p-1, p, p+1; plane p + D0 sits at position (PH + D0 + 1) % 3) are
+// registers, everything else is read from the ring
+template <int PH, int ROW, int PITCH, int PLANE>
+struct PmlColSrc {
+  const double (&col)[PML_R][PML_NRING][3];
+  const double* base[3];  // this thread's row-0 cell in the slots of p-1, p, p+1
+  const double* y;        // passthrough components are read from the state itself
   template <int D0, int D1, int D2>
   __device__ __forceinline__ double rel(int comp, const PmlCell& c) const {
+    static_assert(D0 >= -1 && D0 <= 1, "three planes");
     if (PML_PASSTHROUGH && PML_KIND[comp] != 0) {
       constexpr i64 off =
           D0 * PmlAx<0>::S + D1 * PmlAx<1>::S + D2 * PmlAx<2>::S;
       return PML_LD(y + (i64)comp * PML_NCELLS + c.idx + off);
     }
-    if (D1 == 0 && D2 == 0) return v[pml_ring_index(comp)][D0 + 1];
 #if PML_NDIM == 3
-    return base[D0 + 1][pml_ring_index(comp) * PLANE + D1 * PITCH + D2];
+    constexpr int row = ROW + D1;
+    constexpr bool own = D2 == 0 && row >= 0 && row < PML_R;
+    if constexpr (own) {
+      return col[row][pml_ring_index(comp)][(PH + D0 + 1) % 3];
+    } else {
+      return base[D0 + 1][pml_ring_index(comp) * PLANE + row * PITCH + D2];
+    }
 #else
-    return base[D0 + 1][pml_ring_index(comp) * PLANE + D1];
+    if constexpr (D1 == 0) {
+      return col[0][pml_ring_index(comp)][(PH + D0 + 1) % 3];
+    } else {
+      return base[D0 + 1][pml_ring_index(comp) * PLANE + D1];
+    }
 #endif
   }
 };
 
-__device__ __forceinline__ void pml_mbar_arrive(unsigned bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// waits for the phase of barrier slot (r & 7) that step / plane r completes
-__device__ __forceinline__ void pml_ws_wait(unsigned bars, int r) {
-  const unsigned addr = bars + ((unsigned)r & 7u) * 8u;
-  const unsigned parity = ((unsigned)r >> 3) & 1u;
-  unsigned ok, spins = 0;
-  do {
-    asm volatile(
-        "{\n"
-        "  .reg .pred p;\n"
-        "  mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
-        "  selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity), "r"(0x989680u)  // suspend-time hint (ns)
-        : "memory");
-    // a protocol error must end the launch, not hang the device
-    if (!ok && ++spins > (1u << 22)) __trap();
-  } while (!ok);
-}
-
 template <int MODE>
-__device__ __forceinline__ void pml_ws_body(const PmlFusedArgs& f, double* smem,
-                                            unsigned long long* bars) {
-  const PmlArgs& a = f.s;
-  constexpr bool first = MODE != PML_F_RK4_34;      // stage A's input is y itself
-  constexpr bool pointwise = MODE == PML_F_RK4_34;  // needs y and acc per cell
-  constexpr int NK = PML_NDT > 0 ? PML_NDT : 1;
-  constexpr int S_IN = PML_WS_SIN, S_MID = PML_WS_SMID, S_K = PML_WS_SK;
-  static_assert(S_IN >= 4 && S_IN <= 8 && S_MID >= 3 && S_MID <= 8, "ring depths");
-  static_assert(S_K >= S_MID - 1 && S_K <= 8, "k ring covers the A/B lead");
-  constexpr int IN_SLOT = PML_NRING * PML_IN_PLANE;
-  constexpr int MID_SLOT = PML_NRING * PML_MID_PLANE;
-  constexpr int K_SLOT = NK * PML_OWN_PLANE;
-  // the TMA destination first (128-byte aligned: planes are padded to 16 doubles)
-  double* in_ring = smem;
-  double* mid_ring = in_ring + S_IN * IN_SLOT;
-  double* k_ring = mid_ring + S_MID * MID_SLOT;
+struct PmlMarch {
+  static constexpr bool first = MODE != PML_F_RK4_34;      // stage A's input is y itself
+  static constexpr bool pointwise = MODE == PML_F_RK4_34;  // y and acc rings in use
+  static constexpr int NK = PML_NDT > 0 ? PML_NDT : 1;
+  static constexpr int R = PML_R;
+  static constexpr int D = PML_FDEPTH;  // iterations the TMA copies run ahead
+  // Synchronisation of the warps of a block.  PML_FSYNC == 0: one
+  // __syncthreads() per iteration.  PML_FSYNC == 1: every warp signals the end
+  // of its iteration on an mbarrier and waits, at the top of iteration n, for
+  // all warps to have finished iteration n - LAG: with a 7-point stencil stage
+  // B of plane i - 1 reads its neighbours' stage-A results of that plane only,
+  // which were written two iterations ago (LAG = 2: the warps may drift apart
+  // by a whole iteration before anyone waits); mixed derivatives also read the
+  // neighbours' plane i, written in the previous iteration (LAG = 1).  Every
+  // TMA-fed ring is then one slot deeper, because a slot may only be refilled
+  // once all warps are two iterations past its last use.
+  static constexpr int SLACK = PML_FSYNC ? 1 : 0;
+  static constexpr int LAG = PML_MIXED ? 1 : 2;
+  // ring depths: stage A of iteration i reads input planes i .. i + 2 (stages
+  // 1+2 / midpoint: stage B re-reads the step-start value of plane i - 1 from
+  // it as well), D more planes are in flight
+  static constexpr int NS_IN = (first ? D + 4 : D + 3) + SLACK;
+  static constexpr int NS_Y = D + 3 + SLACK;    // step-start planes i - 1 .. i + 1
+  static constexpr int NS_ACC = D + 1 + SLACK;  // accumulator plane i - 1
+  static constexpr int NB = D + 1 + SLACK;      // one barrier per iteration in flight
+  static constexpr int IN_SLOT = PML_NRING * PML_IN_PLANE;
+  static constexpr int MID_SLOT = PML_NRING * PML_MID_PLANE;
+  static constexpr int YR_SLOT = NK * PML_YR_PLANE;
+  static constexpr int ACC_SLOT = NK * PML_OWN_PLANE;
+  static constexpr unsigned IN_BOX_BYTES = PML_IW * PML_IH * 8;
+  static constexpr unsigned Y_BOX_BYTES = PML_IW * PML_MH * 8;
+  static constexpr unsigned ACC_BOX_BYTES = PML_FTX * PML_FTY * 8;
+  static constexpr int N_IN_BOX = PML_NRING;
+  static constexpr int N_Y_BOX = pointwise ? NK : 0;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ox = blockIdx.x * PML_FTX;  // mesh coordinates of the tile origin
-#if PML_NDIM == 3
-  const int oy = blockIdx.y * PML_FTY;
-  const int chunk = blockIdx.z;
-#else
-  const int oy = 0;
-  const int chunk = blockIdx.y;
-#endif
-  const int zb = chunk * PML_FZC;
-  const int ze = min(zb + PML_FZC, PML_N0);
-  const int nB = ze - zb;
-  const int a_lo = max(zb - 1, 0), a_hi = min(ze, PML_N0 - 1);
-  const int in_lo = max(zb - 2, 0), in_hi = min(ze + 1, PML_N0 - 1);
-  const unsigned full_s = pml_smem_addr(bars);
-  const unsigned adone_s = full_s + 64u, bdone_s = full_s + 128u;
+  const PmlFusedArgs& f;
+  PmlArgs b;  // stage B's view: its own time and table slots
+  double *in_ring, *y_ring, *acc_ring, *mid_ring;
+  unsigned bars_s;
+  // planes of the chunk
+  int zb, ze, a_lo, a_hi, in_lo, in_hi, it0, it1;
+  // this thread's column
+  int i1_0, i2;
+  unsigned in_mask, own_mask;  // bit r: row r is inside the mesh / a tile cell
+  bool all_tile_rows;          // none of this warp's rows is a halo row
+  int path_a_in, path_b_in;    // in-plane part of the variant choice
+  int in_cell, mid_cell, yr_cell, own_cell;
+  i64 idx_b;                   // global cell of row 0 on plane i - 1
+  // this thread's TMA box (at most one per iteration)
+  int job, job_comp, job_x, job_y;
+  unsigned job_ring, job_slot_bytes;
+  const void* job_map;
+  // ring positions of iteration i (advanced once per iteration)
+  unsigned s_in;   // input slot of plane i - 1
+  unsigned s_y;    // step-start slot of plane i - 1
+  unsigned s_acc;  // accumulator slot of plane i - 1
+  unsigned s_bar, phase;
+  unsigned n_it;   // iterations done (PML_FSYNC: slot / parity of the done barriers)
+  // register columns (see PmlColSrc) and stage A's increments K(p) at
+  // position (p - it0) % 3
+  double in_col[PML_R][PML_NRING][3];
+  double mid_col[PML_R][PML_NRING][3];
+  double ka[PML_R][NK][3];
 
-  if (tid == 0) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      pml_mbar_init(full_s + k * 8u, 1);
-      pml_mbar_init(adone_s + k * 8u, PML_NAW);
-      pml_mbar_init(bdone_s + k * 8u, PML_NBW);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __device__ __forceinline__ PmlMarch(const PmlFusedArgs& f_) : f(f_) {}
+
+  static __device__ __forceinline__ unsigned wrap(unsigned x, unsigned n) {
+    return x >= n ? x - n : x;
   }
-  __syncthreads();
 
-  // =========================== loader ====================================
-  if (warp == 0) {
-    if (lane != 0) return;
-    constexpr unsigned IN_BOX_BYTES = PML_IW * PML_IH * 8;
-    const unsigned in_s = pml_smem_addr(in_ring);
-    unsigned s_in = 0;
-#pragma unroll 1
-    for (int r = 0; r < nB + 4; ++r) {
-      const int p = zb - 2 + r;
-      // the slot was last read by stage A of plane r - S_IN + 1
-      if (r - S_IN + 1 >= 1) pml_ws_wait(adone_s, r - S_IN + 1);
-      const unsigned bar = full_s + ((unsigned)r & 7u) * 8u;
-      if (p >= in_lo && p <= in_hi) {
-        pml_mbar_expect_tx(bar, PML_NRING * IN_BOX_BYTES);
+  // everything iteration j reads for the first time: input plane j + 2 (the
+  // first iteration also j and j + 1), step-start plane j + 1 (stage A) and
+  // accumulator plane j - 1 (stage B)
+  __device__ __forceinline__ void fetch(int j, int n_in, unsigned si, unsigned sy,
+                                        unsigned sa, unsigned sb) {
+    const unsigned bar = bars_s + sb * 8u;
+    if (threadIdx.x == 0) {
+      unsigned tx = 0;
+      for (int p = j + 3 - n_in; p <= j + 2; ++p)
+        if (p >= in_lo && p <= in_hi) tx += N_IN_BOX * IN_BOX_BYTES;
+      if (pointwise) {
+        if (j + 1 >= a_lo && j + 1 <= a_hi) tx += N_Y_BOX * Y_BOX_BYTES;
+        if (j - 1 >= zb && j - 1 < ze) tx += N_Y_BOX * ACC_BOX_BYTES;
+      }
+      pml_mbar_expect_tx(bar, tx);
+    }
+    if (job == 0) {
+      // si: slot of plane j + 2
+      for (int k = 0; k < n_in; ++k) {
+        const int p = j + 3 - n_in + k;
+        if (p >= in_lo && p <= in_hi)
+          pml_tma_box(job_ring + wrap(si + NS_IN + 1 - n_in + k, NS_IN) * job_slot_bytes,
+                      job_map, job_x, job_y, p, job_comp, bar);
+      }
+    } else if (job == 1) {
+      if (j + 1 >= a_lo && j + 1 <= a_hi)
+        pml_tma_box(job_ring + sy * job_slot_bytes, job_map, job_x, job_y, j + 1,
+                    job_comp, bar);
+    } else if (job == 2) {
+      if (j - 1 >= zb && j - 1 < ze)
+        pml_tma_box(job_ring + sa * job_slot_bytes, job_map, job_x, job_y, j - 1,
+                    job_comp, bar);
+    }
+  }
+
+  __device__ __forceinline__ void setup(double* smem, unsigned long long* bars) {
+    const PmlArgs& a = f.s;
+    in_ring = smem;  // TMA destinations first: 128-byte aligned planes
+    y_ring = in_ring + NS_IN * IN_SLOT;
+    acc_ring = y_ring + (pointwise ? NS_Y * YR_SLOT : 0);
+    mid_ring = acc_ring + (pointwise ? NS_ACC * ACC_SLOT : 0);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int strip = PML_FHY ? warp % PML_WPR : warp;
+    const int mr0 = PML_FHY ? (warp / PML_WPR) * R : 0;
+    const int mc = strip * 32 + lane;
+    const int ox = blockIdx.x * PML_FTX;  // mesh coordinates of the tile origin
+#if PML_NDIM == 3
+    const int oy = blockIdx.y * PML_FTY;
+    const int chunk = blockIdx.z;
+    i1_0 = oy - 1 + mr0;
+    i2 = ox - 1 + mc;
+    in_mask = own_mask = 0;
+    bool all_in = true, outer_in = true, all_in_b = true, outer_in_b = true;
 #pragma unroll
-        for (int k = 0; k < PML_C; ++k)
-          if (!PML_PASSTHROUGH || PML_KIND[k] == 0)
-            pml_tma_box(in_s + (s_in * IN_SLOT + pml_ring_index(k) * PML_IN_PLANE) * 8u,
-                        f.tm_in, ox - 2, oy - 2 * PML_FHY, p, k, bar);
+    for (int r = 0; r < R; ++r) {
+      const int i1 = i1_0 + r;
+      const bool inp = i1 >= 0 && i1 < PML_N1 && i2 >= 0 && i2 < PML_N2;
+      const bool own = inp && mc >= 1 && mc <= PML_FTX && mr0 + r >= 1 &&
+                       mr0 + r <= PML_FTY;
+      in_mask |= (inp ? 1u : 0u) << r;
+      own_mask |= (own ? 1u : 0u) << r;
+      const bool a1 = i1 > 0 && i1 < PML_N1 - 1, a2 = i2 > 0 && i2 < PML_N2 - 1;
+      all_in = all_in && (!inp || (a1 && a2));
+      outer_in = outer_in && (!inp || a1);
+      all_in_b = all_in_b && (!own || (a1 && a2));
+      outer_in_b = outer_in_b && (!own || a1);
+    }
+    in_cell = (mr0 + 1) * PML_IW + (mc + 1);
+    own_cell = (mr0 - 1) * PML_FTX + (mc - 1);
+    idx_b = (i64)i1_0 * PML_N2 + i2;
+    all_tile_rows = mr0 >= 1 && mr0 + R - 1 <= PML_FTY;
+#else
+    const int oy = 0;
+    const int chunk = blockIdx.y;
+    i1_0 = ox - 1 + mc;
+    i2 = 0;
+    const bool inp = i1_0 >= 0 && i1_0 < PML_N1;
+    const bool own = inp && mc >= 1 && mc <= PML_FTX;
+    in_mask = inp ? 1u : 0u;
+    own_mask = own ? 1u : 0u;
+    const bool a1 = i1_0 > 0 && i1_0 < PML_N1 - 1;
+    const bool all_in = !inp || a1, outer_in = true;
+    const bool all_in_b = !own || a1, outer_in_b = true;
+    in_cell = mc + 1;
+    own_cell = mc - 1;
+    idx_b = (i64)i1_0;
+    all_tile_rows = true;
+#endif
+    mid_cell = mr0 * PML_MW + mc;
+    yr_cell = mr0 * PML_IW + (mc + 1);
+    path_a_in = __all_sync(0xffffffffu, all_in) ? 2
+                : (__all_sync(0xffffffffu, outer_in) ? 1 : 0);
+    path_b_in = __all_sync(0xffffffffu, all_in_b) ? 2
+                : (__all_sync(0xffffffffu, outer_in_b) ? 1 : 0);
+    // components that are not time-stepped are read from the state at the
+    // cell itself: rows outside the mesh must not be evaluated then, which
+    // only the guarded variants ensure
+    if (PML_NALG + PML_NLAP > 0) {
+      if (__any_sync(0xffffffffu, in_mask != (1u << R) - 1u)) path_a_in = min(path_a_in, 1);
+      if (__any_sync(0xffffffffu, own_mask != (1u << R) - 1u)) path_b_in = min(path_b_in, 1);
+    }
+
+    zb = chunk * PML_FZC;
+    ze = min(zb + PML_FZC, PML_N0);
+    a_lo = max(zb - 1, 0);
+    a_hi = min(ze, PML_N0 - 1);
+    in_lo = max(zb - 2, 0);
+    in_hi = min(ze + 1, PML_N0 - 1);
+    it0 = a_lo - 1;
+    it1 = ze;  // iterations: A(i + 1) and B(i - 1)
+    idx_b += (i64)(it0 - 1) * PmlAx<0>::S;
+
+    b = a;
+    b.t_eval = f.t_eval_b;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      b.neu[q] = f.neu_b[q];
+      b.dir[q] = f.dir_b[q];
+    }
+
+    // TMA boxes are dealt out to the warps round-robin (the copy instruction
+    // takes uniform operands, so a warp issues its boxes one lane at a time)
+    constexpr int N_WARPS = PML_F_THREADS / 32;
+    static_assert(N_IN_BOX + 2 * N_Y_BOX <= PML_F_THREADS, "one TMA box per thread");
+    job = -1;
+    job_comp = job_x = job_y = 0;
+    job_ring = job_slot_bytes = 0;
+    job_map = nullptr;
+    int q = warp + N_WARPS * lane;
+    if (q < N_IN_BOX) {
+      job = 0;
+#pragma unroll
+      for (int k = 0; k < PML_C; ++k)
+        if ((!PML_PASSTHROUGH || PML_KIND[k] == 0) && pml_ring_index(k) == q)
+          job_comp = k;
+      job_x = ox - 2;
+      job_y = oy - 2 * PML_FHY;
+      job_ring = pml_smem_addr(in_ring) + (unsigned)q * (PML_IN_PLANE * 8);
+      job_slot_bytes = IN_SLOT * 8;
+      job_map = f.tm_in;
+    } else if (pointwise && (q -= N_IN_BOX) < N_Y_BOX) {
+      job = 1;
+      job_comp = PML_DT_IDX[q];
+      job_x = ox - 2;
+      job_y = oy - PML_FHY;
+      job_ring = pml_smem_addr(y_ring) + (unsigned)q * (PML_YR_PLANE * 8);
+      job_slot_bytes = YR_SLOT * 8;
+      job_map = f.tm_y;
+    } else if (pointwise && (q -= N_Y_BOX) < N_Y_BOX) {
+      job = 2;
+      job_comp = PML_DT_IDX[q];
+      job_x = ox;
+      job_y = oy;
+      job_ring = pml_smem_addr(acc_ring) + (unsigned)q * (PML_OWN_PLANE * 8);
+      job_slot_bytes = ACC_SLOT * 8;
+      job_map = f.tm_acc;
+    }
+
+    bars_s = pml_smem_addr(bars);
+    if (tid == 0) {
+#pragma unroll
+      for (int k = 0; k < NB; ++k) pml_mbar_init(bars_s + k * 8u, 1);
+      // "iteration done" barriers (PML_FSYNC): one arrival per warp
+#pragma unroll
+      for (int k = 0; k < 4; ++k) pml_mbar_init(bars_s + (NB + k) * 8u, N_WARPS);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // Slot numbering: input plane p lives in slot (p - it0 + 1) mod NS_IN, the
+    // step-start plane p in slot (p - it0 + 1) mod NS_Y, the accumulator plane
+    // p in slot (p - it0 + 1) mod NS_ACC (so that "plane i - 1" is the
+    // iteration's running index in all three) and iteration j uses barrier
+    // (j - it0) mod NB.
+    // prologue: the first iteration needs three input planes at once, the
+    // next D - 1 iterations one more each
+    fetch(it0, 3, 3 % NS_IN, 2 % NS_Y, 0, 0);
+#pragma unroll 1
+    for (int d = 1; d < D; ++d)
+      fetch(it0 + d, 1, (3 + d) % NS_IN, (2 + d) % NS_Y, d % NS_ACC, d % NB);
+    s_in = s_y = s_acc = s_bar = phase = 0;
+    n_it = 0;
+
+    // the column's first two planes (it0, it0 + 1: positions 0, 1 of phase 0)
+    pml_mbar_wait(bars_s, 0);
+    const double* p0 = in_ring + (1 % NS_IN) * IN_SLOT + in_cell;
+    const double* p1 = in_ring + (2 % NS_IN) * IN_SLOT + in_cell;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int q2 = 0; q2 < PML_NRING; ++q2) {
+        in_col[r][q2][0] = p0[q2 * PML_IN_PLANE + r * PML_IW];
+        in_col[r][q2][1] = p1[q2 * PML_IN_PLANE + r * PML_IW];
+        in_col[r][q2][2] = 0.0;
+        mid_col[r][q2][0] = mid_col[r][q2][1] = mid_col[r][q2][2] = 0.0;
+      }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int j = 0; j < NK; ++j) ka[r][j][0] = ka[r][j][1] = ka[r][j][2] = 0.0;
+  }
+
+  // ---- stage A on plane p = i + 1, row ROW of this thread
+  template <int PH, int ROW, int IM>
+  __device__ __forceinline__ void a_row(int p, i64 idx_row0, const double* pin_lo,
+                                        const double* pin_c, const double* pin_hi,
+                                        const double* py, double* pm) {
+    const PmlArgs& a = f.s;
+    PmlCell c;
+    c.i0 = p;
+    c.i1 = PML_FHY ? i1_0 + ROW : i1_0;
+    c.i2 = i2;
+    c.idx = idx_row0 + (PML_FHY ? (i64)ROW * PmlAx<1>::S : 0);
+    const PmlColSrc<PH, ROW, PML_IW, PML_IN_PLANE> src{in_col, {pin_lo, pin_c, pin_hi}, a.y};
+    double K[NK];
+    pml_rhs_dt<IM>(a, src, c, a.t_eval, K);
+#pragma unroll
+    for (int j = 0; j < PML_NDT; ++j) {
+      const int k = PML_DT_IDX[j];
+      const double y0 = first ? in_col[ROW][pml_ring_index(k)][(PH + 1) % 3]
+                              : py[j * PML_YR_PLANE + ROW * PML_IW];
+      double ua, kk = 0.0;
+      if (MODE == PML_F_MID) {
+        ua = y0 + (a.dt / 2.0) * K[j];
       } else {
-        pml_mbar_arrive(bar);
+        kk = a.dt * K[j];
+        ua = MODE == PML_F_RK4_12 ? y0 + kk / 2.0 : y0 + kk;
       }
-      if (++s_in == S_IN) s_in = 0;
+      const double v = pml_dirichlet(a.dir, k, c, ua);
+      mid_col[ROW][pml_ring_index(k)][PH % 3] = v;
+      pm[pml_ring_index(k) * PML_MID_PLANE + ROW * PML_MW] = v;
+      ka[ROW][j][(PH + 1) % 3] = kk;
     }
-    return;
-  }
-
-  // ============== compute roles: this lane's cell column ===================
-  const bool role_a = warp <= PML_NAW;
-  const int w = role_a ? warp - 1 : warp - 1 - PML_NAW;
-  const int mr = role_a ? w / PML_WPR : PML_FHY + w / PML_WPR;  // row in the A tile
-  const int mc = (w % PML_WPR) * 32 + lane;
-#if PML_NDIM == 3
-  const int i1 = oy - 1 + mr, i2 = ox - 1 + mc;
-  const bool in_plane = i1 >= 0 && i1 < PML_N1 && i2 >= 0 && i2 < PML_N2;
-  const bool owner = in_plane && mc >= 1 && mc <= PML_FTX && mr >= 1 && mr <= PML_FTY;
-  const int in_cell = (mr + 1) * PML_IW + (mc + 1);
-  const int own_cell = (mr - 1) * PML_FTX + (mc - 1);
-#else
-  const int i1 = ox - 1 + mc, i2 = 0;
-  const bool in_plane = i1 >= 0 && i1 < PML_N1;
-  const bool owner = in_plane && mc >= 1 && mc <= PML_FTX;
-  const int in_cell = mc + 1;
-  const int own_cell = mc - 1;
-#endif
-  const int mid_cell = mr * PML_MW + mc;
-  const i64 idx0 = pml_lin(0, in_plane ? i1 : 0, in_plane ? i2 : 0);
-
-  if (role_a) {
-    // ============================ stage A =================================
-    const int path_in0 = pml_inplane_path(in_plane, i1, i2);
-    PmlMarchSrc<PML_IW, PML_IN_PLANE> src;
-    src.y = a.y;
-    // stage A has no plane 0: the slot's first phase is completed here so
-    // that slot r & 7 is in phase r >> 3 for every plane r
-    if (lane == 0) pml_mbar_arrive(adone_s);
-    // input planes 0 and 1 (steps 0, 1): the column's first two values
-    pml_ws_wait(full_s, 0);
-    pml_ws_wait(full_s, 1);
-#pragma unroll
-    for (int q = 0; q < PML_NRING; ++q) {
-      src.v[q][0] = 0.0;
-      src.v[q][1] = in_ring[q * PML_IN_PLANE + in_cell];
-      src.v[q][2] = in_ring[IN_SLOT + q * PML_IN_PLANE + in_cell];
-    }
-    unsigned s_lo = 0, s_c = 1, s_hi = 2;   // input slots of planes r-1, r, r+1
-    unsigned s_m = 1 % S_MID, s_k = 1 % S_K;  // slots of plane r
-#pragma unroll 1
-    for (int r = 1; r <= nB + 2; ++r) {
-      const int p = zb - 2 + r;
-      const bool active = in_plane && p >= a_lo && p <= a_hi;
-      // stages 3+4: the step-start value comes straight from HBM / L2,
-      // requested before the waits so that it has arrived by the time the
-      // right-hand side is done
-      double y_start[NK];
-      if (pointwise && active) {
-#pragma unroll
-        for (int j = 0; j < PML_NDT; ++j)
-          y_start[j] = PML_LD_ONCE(a.y + (i64)PML_DT_IDX[j] * PML_NCELLS + idx0 +
-                                   (i64)p * PmlAx<0>::S);
-      }
-      pml_ws_wait(full_s, r + 1);
-#pragma unroll
-      for (int q = 0; q < PML_NRING; ++q) {
-        src.v[q][0] = src.v[q][1];
-        src.v[q][1] = src.v[q][2];
-        src.v[q][2] = in_ring[s_hi * IN_SLOT + q * PML_IN_PLANE + in_cell];
-      }
-      // the mid / k slots of plane r were last read by stage B of plane
-      // r - S_MID + 1 (k: r - S_K, not later)
-      if (r - S_MID + 1 >= 2) pml_ws_wait(bdone_s, r - S_MID + 1);
-      if (active) {
-        const int path = (p > 0 && p < PML_N0 - 1) ? path_in0 : 0;
-        PmlCell c;
-        c.i0 = p;
-        c.i1 = i1;
-        c.i2 = i2;
-        c.idx = idx0 + (i64)p * PmlAx<0>::S;
-        src.base[0] = in_ring + s_lo * IN_SLOT + in_cell;
-        src.base[1] = in_ring + s_c * IN_SLOT + in_cell;
-        src.base[2] = in_ring + s_hi * IN_SLOT + in_cell;
-        double K[NK];
-        pml_eval_dt(path, a, src, c, a.t_eval, K);
-        double* slot = mid_ring + s_m * MID_SLOT + mid_cell;
-        double* kslot = k_ring + s_k * K_SLOT + own_cell;
-#pragma unroll
-        for (int j = 0; j < PML_NDT; ++j) {
-          const int k = PML_DT_IDX[j];
-          const double y0 = first ? src.template rel<0, 0, 0>(k, c) : y_start[j];
-          double ua, kk = 0.0;
-          if (MODE == PML_F_MID) {
-            ua = y0 + (a.dt / 2.0) * K[j];
-          } else {
-            kk = a.dt * K[j];
-            ua = MODE == PML_F_RK4_12 ? y0 + kk / 2.0 : y0 + kk;
-          }
-          slot[pml_ring_index(k) * PML_MID_PLANE] = pml_dirichlet(a.dir, k, c, ua);
-          if (MODE != PML_F_MID && owner) kslot[j * PML_OWN_PLANE] = kk;
-        }
 #if PML_NALG + PML_NLAP > 0
-        if (!PML_PASSTHROUGH) {
+    if (!PML_PASSTHROUGH) {
 #pragma unroll
-          for (int k = 0; k < PML_C; ++k) {
-            if (PML_KIND[k] == 0) continue;
-            slot[k * PML_MID_PLANE] = pml_dirichlet(
-                a.dir, k, c, PML_LD(a.y + (i64)k * PML_NCELLS + c.idx));
-          }
-        }
-        if (first && owner && p >= zb && p < ze)
-          pml_first_stage_extras(path, a, src, c);
-#endif
+      for (int k = 0; k < PML_C; ++k) {
+        if (PML_KIND[k] == 0) continue;
+        const double v = pml_dirichlet(
+            a.dir, k, c, PML_LD(a.y + (i64)k * PML_NCELLS + c.idx));
+        mid_col[ROW][k][PH % 3] = v;
+        pm[k * PML_MID_PLANE + ROW * PML_MW] = v;
       }
-      __syncwarp();
-      if (lane == 0) pml_mbar_arrive(adone_s + ((unsigned)r & 7u) * 8u);
-      s_lo = s_c;
-      s_c = s_hi;
-      if (++s_hi == S_IN) s_hi = 0;
-      if (++s_m == S_MID) s_m = 0;
-      if (++s_k == S_K) s_k = 0;
     }
-    return;
+    if (first && ((own_mask >> ROW) & 1u) && p >= zb && p < ze)
+      pml_first_stage_extras(IM == PML_IM_ALL ? 2 : (IM == 0 ? 0 : 1), a, src, c);
+#endif
   }
 
-  // ============================== stage B ===================================
-  PmlArgs b = a;  // stage B sees its own time and table slots
-  b.t_eval = f.t_eval_b;
-#pragma unroll
-  for (int q = 0; q < 6; ++q) {
-    b.neu[q] = f.neu_b[q];
-    b.dir[q] = f.dir_b[q];
-  }
-  const int path_in0 = pml_inplane_path(owner, i1, i2);
-  PmlMarchSrc<PML_MW, PML_MID_PLANE> src;
-  src.y = a.y;
-  if (lane == 0) {  // stage B has no planes 0 and 1 (see stage A)
-    pml_mbar_arrive(bdone_s);
-    pml_mbar_arrive(bdone_s + 8u);
-  }
-  pml_ws_wait(adone_s, 1);
-  pml_ws_wait(adone_s, 2);
-#pragma unroll
-  for (int q = 0; q < PML_NRING; ++q) {
-    src.v[q][0] = 0.0;
-    src.v[q][1] = mid_ring[(1 % S_MID) * MID_SLOT + q * PML_MID_PLANE + mid_cell];
-    src.v[q][2] = mid_ring[(2 % S_MID) * MID_SLOT + q * PML_MID_PLANE + mid_cell];
-  }
-  unsigned s_lo = 1 % S_MID, s_c = 2 % S_MID, s_hi = 3 % S_MID;  // mid slots r-1, r, r+1
-  unsigned s_k = 2 % S_K;                                        // k slot of plane r
-  const i64 cell0 = idx0 + (i64)zb * PmlAx<0>::S;
-  const double* y_at = b.y + cell0;            // step-start state at this cell
-  const double* acc_at = b.acc_in + cell0;
-  double* out_a = (MODE == PML_F_RK4_12 ? b.u_out : b.y_next) + cell0;
-  double* out_b = b.acc_out + cell0;
-#pragma unroll 1
-  for (int r = 2; r <= nB + 1; ++r) {
-    const int p = zb - 2 + r;
-    // pointwise operands straight from HBM / L2 (the step-start value was
-    // fetched for stage A a few planes ago): requested before the wait
-    double y_start[NK], acc_old[NK];
-    if (owner) {
-#pragma unroll
-      for (int j = 0; j < PML_NDT; ++j) {
-        const i64 o = (i64)PML_DT_IDX[j] * PML_NCELLS;
-        y_start[j] = PML_LD_ONCE(y_at + o);
-        acc_old[j] = pointwise ? PML_LD_ONCE(acc_at + o) : 0.0;
-      }
+  template <int PH, int IM, bool GUARD, int ROW = 0>
+  __device__ __forceinline__ void a_rows(int p, i64 idx_row0, const double* pin_lo,
+                                         const double* pin_c, const double* pin_hi,
+                                         const double* py, double* pm) {
+    if constexpr (ROW < R) {
+      if (!GUARD || ((in_mask >> ROW) & 1u))
+        a_row<PH, ROW, IM>(p, idx_row0, pin_lo, pin_c, pin_hi, py, pm);
+      a_rows<PH, IM, GUARD, ROW + 1>(p, idx_row0, pin_lo, pin_c, pin_hi, py, pm);
     }
-    pml_ws_wait(adone_s, r + 1);
+  }
+
+  // ---- stage B on plane p = i - 1, row ROW of this thread
+  template <int PH, int ROW, int IM>
+  __device__ __forceinline__ void b_row(int p, bool store, const double* pm_lo,
+                                        const double* pm_c, const double* pm_hi,
+                                        const double* py, const double* pacc,
+                                        double* out_a, double* out_b) {
+    PmlCell c;
+    c.i0 = p;
+    c.i1 = PML_FHY ? i1_0 + ROW : i1_0;
+    c.i2 = i2;
+    c.idx = idx_b + (PML_FHY ? (i64)ROW * PmlAx<1>::S : 0);
+    const PmlColSrc<PH, ROW, PML_MW, PML_MID_PLANE> src{mid_col, {pm_lo, pm_c, pm_hi}, f.s.y};
+    double K[NK];
+    pml_rhs_dt<IM>(b, src, c, b.t_eval, K);
 #pragma unroll
-    for (int q = 0; q < PML_NRING; ++q) {
-      src.v[q][0] = src.v[q][1];
-      src.v[q][1] = src.v[q][2];
-      src.v[q][2] = mid_ring[s_hi * MID_SLOT + q * PML_MID_PLANE + mid_cell];
-    }
-    if (owner) {
-      const int path = (p > 0 && p < PML_N0 - 1) ? path_in0 : 0;
-      PmlCell c;
-      c.i0 = p;
-      c.i1 = i1;
-      c.i2 = i2;
-      c.idx = idx0 + (i64)p * PmlAx<0>::S;
-      src.base[0] = mid_ring + s_lo * MID_SLOT + mid_cell;
-      src.base[1] = mid_ring + s_c * MID_SLOT + mid_cell;
-      src.base[2] = mid_ring + s_hi * MID_SLOT + mid_cell;
-      double K[NK];
-      pml_eval_dt(path, b, src, c, b.t_eval, K);
-      const double* kr = k_ring + s_k * K_SLOT + own_cell;
-#pragma unroll
-      for (int j = 0; j < PML_NDT; ++j) {
-        const int k = PML_DT_IDX[j];
-        const i64 o = (i64)k * PML_NCELLS;
-        const double y0 = y_start[j];
-        if (MODE == PML_F_RK4_12) {
-          const double kk = b.dt * K[j];
-          PML_ST(out_b + o, kr[j * PML_OWN_PLANE] + 2.0 * kk);
-          PML_ST(out_a + o, pml_dirichlet(b.dir, k, c, y0 + kk / 2.0));
-        } else if (MODE == PML_F_RK4_34) {
-          const double kk = b.dt * K[j];
-          const double acc = acc_old[j] + 2.0 * kr[j * PML_OWN_PLANE];
-          PML_ST(out_a + o, pml_dirichlet(b.dir, k, c, y0 + pml_div6(acc + kk)));
-        } else {
-          PML_ST(out_a + o, pml_dirichlet(b.dir, k, c, y0 + b.dt * K[j]));
+    for (int j = 0; j < PML_NDT; ++j) {
+      const int k = PML_DT_IDX[j];
+      const i64 o = (i64)k * PML_NCELLS + c.idx;
+      // the step-start value: stages 1+2 / midpoint re-read it from the input
+      // ring (plane i - 1 is still there), stages 3+4 from the y ring
+      const double y0 = first ? py[pml_ring_index(k) * PML_IN_PLANE + ROW * PML_IW]
+                              : py[j * PML_YR_PLANE + ROW * PML_IW];
+      const double k_a = ka[ROW][j][(PH + 2) % 3];
+      if (MODE == PML_F_RK4_12) {
+        const double kk = b.dt * K[j];
+        const double acc = k_a + 2.0 * kk;
+        const double u = pml_dirichlet(b.dir, k, c, y0 + kk / 2.0);
+        if (store) {
+          PML_ST(out_b + o, acc);
+          PML_ST(out_a + o, u);
         }
+      } else if (MODE == PML_F_RK4_34) {
+        const double kk = b.dt * K[j];
+        const double acc = pacc[j * PML_OWN_PLANE + ROW * PML_FTX] + 2.0 * k_a;
+        const double u = pml_dirichlet(b.dir, k, c, y0 + pml_div6(acc + kk));
+        if (store) PML_ST(out_a + o, u);
+      } else {
+        const double u = pml_dirichlet(b.dir, k, c, y0 + b.dt * K[j]);
+        if (store) PML_ST(out_a + o, u);
       }
+    }
 #if PML_NALG + PML_NLAP > 0
-      if (MODE == PML_F_RK4_12 && !PML_PASSTHROUGH) {
+    if (MODE == PML_F_RK4_12 && !PML_PASSTHROUGH && store) {
 #pragma unroll
-        for (int k = 0; k < PML_C; ++k) {
-          if (PML_KIND[k] == 0) continue;
-          const i64 o = (i64)k * PML_NCELLS + c.idx;
-          b.u_out[o] = pml_dirichlet(b.dir, k, c, PML_LD(b.y + o));
-        }
+      for (int k = 0; k < PML_C; ++k) {
+        if (PML_KIND[k] == 0) continue;
+        const i64 o = (i64)k * PML_NCELLS + c.idx;
+        b.u_out[o] = pml_dirichlet(b.dir, k, c, PML_LD(b.y + o));
       }
-#endif
     }
+#endif
+  }
+
+  template <int PH, int IM, bool GUARD, int ROW = 0>
+  __device__ __forceinline__ void b_rows(int p, const double* pm_lo, const double* pm_c,
+                                         const double* pm_hi, const double* py,
+                                         const double* pacc, double* out_a,
+                                         double* out_b) {
+    if constexpr (ROW < R) {
+      const bool own = (own_mask >> ROW) & 1u;
+      if (!GUARD || own)
+        b_row<PH, ROW, IM>(p, own, pm_lo, pm_c, pm_hi, py, pacc, out_a, out_b);
+      b_rows<PH, IM, GUARD, ROW + 1>(p, pm_lo, pm_c, pm_hi, py, pacc, out_a, out_b);
+    }
+  }
+
+  // One iteration at phase PH = (i - it0) mod 3: stage B on plane i - 1, then
+  // stage A on plane i + 1.
+  template <int PH>
+  __device__ __forceinline__ void iteration(int i) {
+    const PmlArgs& a = f.s;
+    if (PML_FSYNC && n_it >= (unsigned)LAG) {
+      const unsigned m = n_it - LAG;
+      pml_mbar_wait(bars_s + (NB + (m & 3u)) * 8u, (m >> 2) & 1u);
+    }
+    // the slots whose last readers are known to be done are refilled
+    if (i + D <= it1)
+      fetch(i + D, 1, wrap(s_in + D + 3, NS_IN), wrap(s_y + D + 2, NS_Y),
+            wrap(s_acc + D, NS_ACC), wrap(s_bar + D, NB));
+    // ring addresses of this iteration
+    const double* pin_b = in_ring + s_in * IN_SLOT + in_cell;  // plane i - 1
+    const double* pin_lo = in_ring + wrap(s_in + 1, NS_IN) * IN_SLOT + in_cell;
+    const double* pin_c = in_ring + wrap(s_in + 2, NS_IN) * IN_SLOT + in_cell;
+    const double* pin_hi = in_ring + wrap(s_in + 3, NS_IN) * IN_SLOT + in_cell;
+    const double* py_b = y_ring + s_y * YR_SLOT + yr_cell;                 // plane i - 1
+    const double* py_a = y_ring + wrap(s_y + 2, NS_Y) * YR_SLOT + yr_cell;  // plane i + 1
+    const double* pacc = acc_ring + s_acc * ACC_SLOT + own_cell;
+    const double* pm_lo = mid_ring + ((i - 2) & 3) * MID_SLOT + mid_cell;
+    const double* pm_c = mid_ring + ((i - 1) & 3) * MID_SLOT + mid_cell;
+    const double* pm_hi = mid_ring + (i & 3) * MID_SLOT + mid_cell;
+    double* pm_new = mid_ring + ((i + 1) & 3) * MID_SLOT + mid_cell;
+
+    pml_mbar_wait(bars_s + s_bar * 8u, phase);
+    // the column's new plane i + 2
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int q = 0; q < PML_NRING; ++q)
+        in_col[r][q][(PH + 2) % 3] = pin_hi[q * PML_IN_PLANE + r * PML_IW];
+
+    // ---- stage B on plane i - 1 (tile cells), neighbours from the stage-A ring
+    {
+      const int p = i - 1;
+      if (p >= zb && p < ze) {
+        const int path = (p > 0 && p < PML_N0 - 1) ? path_b_in : 0;
+        double* out_a = MODE == PML_F_RK4_12 ? b.u_out : b.y_next;
+        const double* py = first ? pin_b : py_b;
+        if (path == 2 && all_tile_rows)
+          b_rows<PH, PML_IM_ALL, false>(p, pm_lo, pm_c, pm_hi, py, pacc, out_a, b.acc_out);
+        else if (path == 2)  // first / last row group: its halo row is skipped
+          b_rows<PH, PML_IM_ALL, true>(p, pm_lo, pm_c, pm_hi, py, pacc, out_a, b.acc_out);
+        else if (path == 1)
+          b_rows<PH, PML_IM_OUTER, true>(p, pm_lo, pm_c, pm_hi, py, pacc, out_a, b.acc_out);
+        else
+          b_rows<PH, 0, true>(p, pm_lo, pm_c, pm_hi, py, pacc, out_a, b.acc_out);
+      }
+    }
+    // ---- stage A on plane i + 1 (tile + halo 1), neighbours from the input ring
+    {
+      const int p = i + 1;
+      if (p >= a_lo && p <= a_hi) {
+        const int path = (p > 0 && p < PML_N0 - 1) ? path_a_in : 0;
+        const i64 idx_row0 = idx_b + 2 * PmlAx<0>::S;
+        if (path == 2)
+          a_rows<PH, PML_IM_ALL, false>(p, idx_row0, pin_lo, pin_c, pin_hi, py_a, pm_new);
+        else if (path == 1)
+          a_rows<PH, PML_IM_OUTER, true>(p, idx_row0, pin_lo, pin_c, pin_hi, py_a, pm_new);
+        else
+          a_rows<PH, 0, true>(p, idx_row0, pin_lo, pin_c, pin_hi, py_a, pm_new);
+      }
+    }
+    idx_b += PmlAx<0>::S;
+    s_in = wrap(s_in + 1, NS_IN);
+    s_y = wrap(s_y + 1, NS_Y);
+    s_acc = wrap(s_acc + 1, NS_ACC);
+    if (++s_bar == NB) {
+      s_bar = 0;
+      phase ^= 1u;
+    }
+#if PML_FSYNC
     __syncwarp();
-    if (lane == 0) pml_mbar_arrive(bdone_s + ((unsigned)r & 7u) * 8u);
-    y_at += PmlAx<0>::S;
-    acc_at += PmlAx<0>::S;
-    out_a += PmlAx<0>::S;
-    out_b += PmlAx<0>::S;
-    s_lo = s_c;
-    s_c = s_hi;
-    if (++s_hi == S_MID) s_hi = 0;
-    if (++s_k == S_K) s_k = 0;
+    if ((threadIdx.x & 31) == 0)
+      pml_mbar_arrive(bars_s + (NB + (n_it & 3u)) * 8u);
+    ++n_it;
+#else
+    __syncthreads();
+#endif
   }
-}
 
-#define PML_WS_KERNEL(NAME, MODE)                                             \
+  __device__ __forceinline__ void run() {
+#pragma unroll 1
+    for (int i = it0; i <= it1; i += 3) {
+      iteration<0>(i);
+      if (i + 1 <= it1) iteration<1>(i + 1);
+      if (i + 2 <= it1) iteration<2>(i + 2);
+    }
+  }
+};
+
+#define PML_MARCH_KERNEL(NAME, MODE)                                          \
   extern "C" __global__ void __launch_bounds__(PML_F_THREADS, PML_FMIN_BLOCKS) \
       NAME(const __grid_constant__ PmlFusedArgs f) {                         \
     extern __shared__ __align__(128) double pml_ring[];                       \
-    __shared__ unsigned long long pml_bars[24];                               \
-    pml_ws_body<MODE>(f, pml_ring, pml_bars);                                 \
+    __shared__ unsigned long long pml_bars[PML_FDEPTH + 2 + 4];               \
+    PmlMarch<MODE> m(f);                                                      \
+    m.setup(pml_ring, pml_bars);                                              \
+    m.run();                                                                  \
   }
 
-PML_WS_KERNEL(pml_fused_rk4_12, PML_F_RK4_12)
-PML_WS_KERNEL(pml_fused_rk4_34, PML_F_RK4_34)
-PML_WS_KERNEL(pml_fused_mid, PML_F_MID)
+PML_MARCH_KERNEL(pml_fused_rk4_12, PML_F_RK4_12)
+PML_MARCH_KERNEL(pml_fused_rk4_34, PML_F_RK4_34)
+PML_MARCH_KERNEL(pml_fused_mid, PML_F_MID)
 #endif  // PML_FUSED == 2
 
 // ---------------------------------------------------------------------------

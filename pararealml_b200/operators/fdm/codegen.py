@@ -82,6 +82,7 @@ class ProblemSpec:
     kinds: Sequence[str]  # LHS kind name per equation
     neu_mask: int = 0  # bit (axis * 2 + side): a Neumann table exists
     dir_mask: int = 0
+    neu_zero_mask: int = 0  # ... and holds 0.0 everywhere (static zero flux)
     passthrough: bool = False
     coherent_loads: bool = False
     eval_only: bool = False  # the differentiator entry points
@@ -143,12 +144,14 @@ class FusedTile:
     smem_first: int  # dynamic shared memory of the stage 1+2 / midpoint kernels
     smem_pointwise: int  # ... of the stage 3+4 kernel (adds y and acc rings)
     min_blocks: int
-    #: 1 = every thread runs both stages, one __syncthreads per plane;
-    #: 2 = warp-specialised pipeline (loader / stage-A / stage-B warps)
+    #: 1 = one thread per cell of the stage-A tile, every stencil operand read
+    #: from shared memory; 2 = column-marching: a thread owns ``rows`` rows of
+    #: one column and keeps three planes of both stages' inputs in registers
     variant: int = 1
-    #: ring depths of the warp-specialised variant: input planes, stage-A
-    #: result planes, stage-A increments
-    rings: Tuple[int, int, int] = (5, 8, 7)
+    rows: int = 1
+    #: marching variant: 0 = __syncthreads per plane, 1 = per-warp mbarrier
+    #: arrivals with one plane of slack (rings one slot deeper)
+    sync: int = 0
 
 
 SMEM_PER_BLOCK_MAX = 227 * 1024
@@ -177,9 +180,9 @@ def default_fused(shape, y_dim, n_dt=None, passthrough=False) -> Optional[FusedT
         return None
     variant = int(os.environ.get("PML_FVARIANT", "2"))
     if variant == 2:
-        ws = _warp_specialised_tile(shape, y_dim, n_dt, passthrough)
-        if ws is not None:
-            return ws
+        tile = _marching_tile(shape, y_dim, n_dt, passthrough)
+        if tile is not None:
+            return tile
     if os.environ.get("PML_FTILE"):
         tx, ty = (int(v) for v in os.environ["PML_FTILE"].split(","))
     elif nd == 3:
@@ -253,15 +256,17 @@ def default_fused(shape, y_dim, n_dt=None, passthrough=False) -> Optional[FusedT
     return FusedTile(tx, ty, zc, depth, threads, first, pointwise, min_blocks)
 
 
-def _warp_specialised_tile(shape, y_dim, n_dt, passthrough) -> Optional[FusedTile]:
-    """Geometry of the warp-specialised stage-pair kernels: rows of the
+def _marching_tile(shape, y_dim, n_dt, passthrough) -> Optional[FusedTile]:
+    """Geometry of the column-marching stage-pair kernels: rows of the
     stage-A tile (tile + halo 1) are whole warps, so the tile is 32 k - 2
-    cells wide; one loader warp, one stage-A warp per 32 cells of every
-    stage-A row, one stage-B warp per 32 cells of every tile row; one thread
-    block per SM (3-D) with ring depths that fit its shared memory."""
+    cells wide; a thread owns ``rows`` consecutive rows of one column (3-D
+    meshes), so the stage-A tile is ``rows * row groups`` rows high."""
     nd = len(shape)
     hy = 1 if nd == 3 else 0
     n_ring = n_dt if passthrough else y_dim
+    depth = int(os.environ.get("PML_FDEPTH", "2"))
+    rows = int(os.environ.get("PML_FROWS", "2")) if nd == 3 else 1
+    sync = int(os.environ.get("PML_FSYNC", "0"))
 
     def pad16(n):
         return -(-n // 16) * 16
@@ -269,7 +274,8 @@ def _warp_specialised_tile(shape, y_dim, n_dt, passthrough) -> Optional[FusedTil
     if os.environ.get("PML_FTILE"):
         tx, ty = (int(v) for v in os.environ["PML_FTILE"].split(","))
     elif nd == 3:
-        tx, ty = 30, 8
+        # 8 row groups: 8 warps of 32 columns
+        tx, ty = 30, 8 * rows - 2
     else:
         tx, ty = 126, 1
     if nd == 2:
@@ -278,49 +284,56 @@ def _warp_specialised_tile(shape, y_dim, n_dt, passthrough) -> Optional[FusedTil
     tx = min(tx, 32 * -(-(shape[-1] + 2) // 32) - 2)
     tx = max(30, 32 * ((tx + 2) // 32) - 2)
     if nd == 3:
-        ty = max(1, min(ty, shape[1]))
-    rings = tuple(
-        int(v) for v in os.environ.get("PML_FRINGS", "5,8,7").split(",")
-    )
+        # whole row groups, not (much) higher than the mesh
+        ty = max(rows, min(ty, rows * -(-(shape[1] + 2) // rows)))
+        ty = rows * -(-(ty + 2) // rows) - 2
+        if ty < 1:
+            return None
 
-    def geometry(tx, ty, rings):
-        s_in, s_mid, s_k = rings
+    def geometry(tx, ty, depth):
         mw, mh = tx + 2, ty + 2 * hy
         iw, ih = tx + 4, ty + 4 * hy
-        wpr = mw // 32
-        threads = 32 * (1 + wpr * mh + wpr * ty)
+        threads = 32 * (mw // 32) * (mh // rows)
         in_slot = n_ring * pad16(iw * ih)
         mid_slot = n_ring * mw * mh
-        k_slot = n_dt * pad16(tx * ty)
-        first = 8 * (s_in * in_slot + s_mid * mid_slot + s_k * k_slot)
-        return threads, first, first
+        y_slot = n_dt * pad16(iw * mh)
+        acc_slot = n_dt * pad16(tx * ty)
+        pad = mw + 8  # unguarded (interior) rows read one row past the ring
+        first = 8 * ((depth + 4 + sync) * in_slot + 4 * mid_slot + pad)
+        pointwise = 8 * ((depth + 3 + sync) * (in_slot + y_slot)
+                         + (depth + 1 + sync) * acc_slot + 4 * mid_slot + pad)
+        return threads, first, pointwise
 
     while True:
-        threads, first, pointwise = geometry(tx, ty, rings)
+        threads, first, pointwise = geometry(tx, ty, depth)
         if (threads <= 1024 and tx + 4 <= 256
                 and max(first, pointwise) + 1024 <= SMEM_PER_BLOCK_MAX):
             break
-        if nd == 3 and ty > 2:
-            ty -= 2 if ty > 4 else 1
+        if depth > 1:
+            depth -= 1
+        elif nd == 3 and ty + 2 > 2 * rows:
+            ty -= rows
         elif tx > 30:
             tx -= 32
         else:
             return None
     tiles = -(-shape[-1] // tx) * (-(-shape[1] // ty) if nd == 3 else 1)
-    # resident blocks per SM: shared memory, threads, and >= 80 registers
+    # resident blocks per SM: shared memory, threads, and registers (a thread
+    # holds 2 x 3 planes of its rows' components plus stage A's increments)
+    regs = 64 + 2 * rows * (6 * n_ring + 3 * n_dt)
     per_sm = max(1, min(SMEM_PER_SM // (max(first, pointwise) + 1024),
-                        2048 // threads, 65536 // (80 * threads)))
+                        2048 // threads, 65536 // (min(regs, 255) * threads)))
     if os.environ.get("PML_FZC"):
         zc = int(os.environ["PML_FZC"])
     else:
-        # the pipeline fills and drains once per chunk (~4 planes): long
-        # chunks, but enough thread blocks for ~6 waves
+        # a chunk recomputes two planes of stage A: long chunks, but enough
+        # thread blocks for ~6 waves
         chunks = max(1, -(-(6 * N_SMS * per_sm) // tiles))
-        zc = min(128, max(32, -(-shape[0] // chunks)))
+        zc = min(128, max(32 if nd == 3 else 16, -(-shape[0] // chunks)))
     zc = max(1, min(zc, shape[0]))
     min_blocks = int(os.environ.get("PML_FMIN_BLOCKS", str(per_sm)))
-    return FusedTile(tx, ty, zc, 1, threads, first, pointwise, min_blocks,
-                     variant=2, rings=rings)
+    return FusedTile(tx, ty, zc, depth, threads, first, pointwise, min_blocks,
+                     variant=2, rows=rows, sync=sync)
 
 
 class _LeafBuilder:
@@ -653,6 +666,7 @@ def generate_source(spec: ProblemSpec) -> str:
         f"#define PML_COORD {COORD_CODES[spec.coord]}",
         f"#define PML_NEU_MASK {spec.neu_mask}",
         f"#define PML_DIR_MASK {spec.dir_mask}",
+        f"#define PML_NEU_ZERO_MASK {spec.neu_zero_mask & spec.neu_mask}",
         f"#define PML_PASSTHROUGH {int(spec.passthrough)}",
         f"#define PML_COHERENT_LOADS {int(spec.coherent_loads or spec.small_threads > 0)}",
         f"#define PML_SMALL {int(spec.small_threads > 0)}",
@@ -669,13 +683,8 @@ def generate_source(spec: ProblemSpec) -> str:
         f"#define PML_FDEPTH {fused.depth if fused else 1}",
         f"#define PML_F_THREADS {fused.threads if fused else 32}",
         f"#define PML_FMIN_BLOCKS {fused.min_blocks if fused else 1}",
-        *(
-            f"#define PML_WS_{name} {value}"
-            for name, value in zip(
-                ("SIN", "SMID", "SK"),
-                fused.rings if (fused and fused.variant == 2) else (5, 8, 7),
-            )
-        ),
+        f"#define PML_FROWS {fused.rows if fused else 1}",
+        f"#define PML_FSYNC {fused.sync if fused else 0}",
         f"#define PML_ZREP {max(1, int(spec.zrep))}",
         f"#define PML_JREP {JACOBI_REP}",
         f"#define PML_BX {block[0]}",
@@ -707,6 +716,11 @@ def generate_source(spec: ProblemSpec) -> str:
     )
     with open(TEMPLATE_PATH) as fh:
         template = fh.read()
+    # mixed second derivatives read the in-plane neighbours of the planes
+    # above and below (the marching stage-pair kernels wait accordingly)
+    prelude = prelude.replace(
+        "#define PML_FUSED ",
+        f"#define PML_MIXED {int('pml_d2m_at<' in rhs_code)}\n#define PML_FUSED ", 1)
     return prelude + template.replace("PML_GENERATED_RHS", rhs_code)
 
 

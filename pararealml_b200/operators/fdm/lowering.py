@@ -27,6 +27,9 @@ class LoweredProblem:
     kinds: List[str]
     neu_mask: int = 0
     dir_mask: int = 0
+    #: faces whose (static) Neumann table is 0.0 for every cell and component
+    #: (zero-flux walls): the kernels then need no table look-ups there
+    neu_zero_mask: int = 0
     # face (axis * 2 + side) -> is the boundary condition static
     face_static: Dict[int, bool] = field(default_factory=dict)
     face_cells: Dict[int, int] = field(default_factory=dict)
@@ -61,6 +64,7 @@ class LoweredProblem:
             kinds=self.kinds,
             neu_mask=self.neu_mask,
             dir_mask=self.dir_mask,
+            neu_zero_mask=self.neu_zero_mask & self.neu_mask,
             **overrides,
         )
 
@@ -158,6 +162,9 @@ def lower_problem(cp) -> LoweredProblem:
                 low.neu_mask |= 1 << f
                 if bc.is_static:
                     low.static_neu[f] = _flat(static_d[axis][side])
+                    # (NaN = unconstrained cell compares unequal)
+                    if np.all(low.static_neu[f] == 0.0):
+                        low.neu_zero_mask |= 1 << f
             if bc.has_y_condition:
                 low.dir_mask |= 1 << f
                 if bc.is_static:

@@ -60,6 +60,7 @@ def slab_lowered(low: LoweredProblem, lo: int, hi: int) -> LoweredProblem:
     # a face of axis 0 exists only where the slab touches the mesh face
     drop = (0 if lo == 0 else 1) | (0 if hi == n0 else 2)
     sub.neu_mask = low.neu_mask & ~drop
+    sub.neu_zero_mask = low.neu_zero_mask & ~drop
     sub.dir_mask = low.dir_mask & ~drop
     cells = int(np.prod(shape))
     for f in range(2 * len(shape)):

@@ -120,20 +120,28 @@ def test_product_path_fails_loudly_without_a_gpu():
     [((512, 512, 512), 3), ((64, 48, 40), 1), ((4096, 4096), 3), ((150, 600), 1),
      ((20, 21, 22), 6), ((9, 9, 4), 2)],
 )
-def test_fused_tile_fits_the_hardware(shape, y_dim, monkeypatch):
+@pytest.mark.parametrize("variant", [1, 2])
+def test_fused_tile_fits_the_hardware(shape, y_dim, variant, monkeypatch):
     """Geometry of the fused stage-pair kernels: thread, TMA box and shared
     memory limits of sm_100a hold for every mesh the default rule accepts."""
-    for key in ("PML_FUSE", "PML_FTILE", "PML_FDEPTH", "PML_FZC", "PML_FMIN_BLOCKS"):
+    for key in ("PML_FUSE", "PML_FTILE", "PML_FDEPTH", "PML_FZC", "PML_FMIN_BLOCKS",
+                "PML_FROWS", "PML_FSYNC"):
         monkeypatch.delenv(key, raising=False)
+    monkeypatch.setenv("PML_FVARIANT", str(variant))
     tile = codegen.default_fused(shape, y_dim, y_dim, False)
-    assert tile is not None
+    assert tile is not None and tile.variant == variant
     hy = 1 if len(shape) == 3 else 0
     assert tile.tx % 2 == 0 and tile.tx + 4 <= 256
-    assert (tile.tx + 2) * (tile.ty + 2 * hy) <= tile.threads <= 1024
+    # one thread per cell of the stage-A tile, or per ``rows`` cells of a column
+    assert (tile.tx + 2) * (tile.ty + 2 * hy) <= tile.threads * tile.rows
+    assert tile.threads <= 1024
+    if variant == 2:
+        assert (tile.tx + 2) % 32 == 0 and (tile.ty + 2 * hy) % tile.rows == 0
     assert tile.threads % 32 == 0
     assert tile.smem_first <= tile.smem_pointwise <= 227 * 1024 - 2048
     assert tile.min_blocks * (tile.smem_pointwise + 1024) <= 228 * 1024
-    assert tile.min_blocks * tile.threads * 96 <= 65536 or tile.min_blocks == 1
+    min_regs = 96 if variant == 1 else 80
+    assert tile.min_blocks * tile.threads * min_regs <= 65536 or tile.min_blocks == 1
     assert 1 <= tile.zc <= shape[0]
 
 
