@@ -57,8 +57,9 @@ typedef struct pml_workspace {
   double* lap_rhs;   /* n_lap * n_cells */
   double* jac_a;     /* n_lap * n_cells */
   double* jac_b;     /* n_lap * n_cells */
-  double* partials;  /* one double per thread block */
-  int* flags;        /* 3 ints: done, sweeps, block ticket of the sweep kernel */
+  double* partials;  /* max(2, one double per thread block of the stage grid) */
+  int* flags;        /* 4 ints: done, sweeps, block ticket of the sweep kernel,
+                        barrier counter of the persistent Jacobi loop */
   double* t_dev;     /* step start times for the single-block kernel */
   long long t_capacity; /* doubles available at t_dev */
 } pml_workspace;
@@ -118,6 +119,15 @@ int pml_fdm_phase(pml_plan* plan, int integrator, const pml_workspace* ws,
                   const double* y_dev, double* y_next_dev, double t, double d_t,
                   long long slot0, int phase, double** fresh_out_dev,
                   void* stream);
+/* The same for the planes [z_begin, z_end) of axis 0 only (stage-pair kernels;
+ * z_end < 0: up to the last plane): a slab-decomposed caller launches the
+ * planes its neighbours are waiting for first and exchanges them while the
+ * launch of the remaining planes runs.  The launches of one phase may be issued
+ * in any order; together they must cover every plane exactly once. */
+int pml_fdm_phase_planes(pml_plan* plan, int integrator, const pml_workspace* ws,
+                         const double* y_dev, double* y_next_dev, double t,
+                         double d_t, long long slot0, int phase, int z_begin,
+                         int z_end, double** fresh_out_dev, void* stream);
 
 /* One evaluation of the generated right-hand sides (differentiator entry
  * points, numerical_differentiator.py:114-870). */

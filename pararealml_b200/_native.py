@@ -135,6 +135,13 @@ SYMBOLS = {
             c_double, c_longlong, c_int, POINTER(c_void_p), c_void_p,
         ],
     ),
+    "pml_fdm_phase_planes": (
+        c_int,
+        [
+            c_void_p, c_int, POINTER(Workspace), c_void_p, c_void_p, c_double,
+            c_double, c_longlong, c_int, c_int, c_int, POINTER(c_void_p), c_void_p,
+        ],
+    ),
     "pml_eval_rhs": (
         c_int, [c_void_p, c_void_p, c_void_p, c_double, c_longlong, c_void_p]
     ),

@@ -578,6 +578,10 @@ struct PmlFusedArgs {
   double t_eval_b;  // stage B evaluation time
   const double* neu_b[6];  // stage B boundary tables
   const double* dir_b[6];
+  // planes [z_begin, z_end) of axis 0 this launch produces (the whole mesh, or
+  // a part of it when a slab-decomposed caller launches the planes next to its
+  // neighbours first); thread blocks cut the range into chunks of PML_FZC
+  int z_begin, z_end;
 };
 
 // in-plane geometry: "x" is the contiguous mesh axis, "y" axis 1 of a 3-D mesh
@@ -743,8 +747,8 @@ __device__ __forceinline__ void pml_fused_body(const PmlFusedArgs& f,
 
   // ---- planes: stage B works on [zb, ze), stage A on one more plane on each
   // side, the input ring on two more
-  const int zb = chunk * PML_FZC;
-  const int ze = min(zb + PML_FZC, PML_N0);
+  const int zb = f.z_begin + chunk * PML_FZC;
+  const int ze = min(zb + PML_FZC, f.z_end);
   const int a_lo = max(zb - 1, 0), a_hi = min(ze, PML_N0 - 1);
   const int in_lo = max(zb - 2, 0), in_hi = min(ze + 1, PML_N0 - 1);
   const int it0 = a_lo - 1, it1 = ze;  // iterations: A(i + 1) and B(i - 1)
@@ -1271,8 +1275,8 @@ struct PmlMarch {
       if (__any_sync(0xffffffffu, own_mask != (1u << R) - 1u)) path_b_in = min(path_b_in, 1);
     }
 
-    zb = chunk * PML_FZC;
-    ze = min(zb + PML_FZC, PML_N0);
+    zb = f.z_begin + chunk * PML_FZC;
+    ze = min(zb + PML_FZC, f.z_end);
     a_lo = max(zb - 1, 0);
     a_hi = min(ze, PML_N0 - 1);
     in_lo = max(zb - 2, 0);
@@ -1539,7 +1543,7 @@ struct PmlMarch {
           b_rows<PH, PML_IM_ALL, false>(p, pm_lo, pm_c, pm_hi, py, pacc, out_a, b.acc_out);
         else if (path == 2)  // first / last row group: its halo row is skipped
           b_rows<PH, PML_IM_ALL, true>(p, pm_lo, pm_c, pm_hi, py, pacc, out_a, b.acc_out);
-        else if (path == 1)
+        else if (PML_F_PATH1 && path == 1)
           b_rows<PH, PML_IM_OUTER, true>(p, pm_lo, pm_c, pm_hi, py, pacc, out_a, b.acc_out);
         else
           b_rows<PH, 0, true>(p, pm_lo, pm_c, pm_hi, py, pacc, out_a, b.acc_out);
@@ -1553,7 +1557,7 @@ struct PmlMarch {
         const i64 idx_row0 = idx_b + 2 * PmlAx<0>::S;
         if (path == 2)
           a_rows<PH, PML_IM_ALL, false>(p, idx_row0, pin_lo, pin_c, pin_hi, py_a, pm_new);
-        else if (path == 1)
+        else if (PML_F_PATH1 && path == 1)
           a_rows<PH, PML_IM_OUTER, true>(p, idx_row0, pin_lo, pin_c, pin_hi, py_a, pm_new);
         else
           a_rows<PH, 0, true>(p, idx_row0, pin_lo, pin_c, pin_hi, py_a, pm_new);
@@ -1764,28 +1768,49 @@ extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ)
 
 // cell of repetition `rep`: every thread walks PML_JREP cells along axis 0, so
 // that their loads are in flight together and the block reduction is amortised
-__device__ __forceinline__ bool pml_jacobi_cell(PmlCell& c, int rep) {
+__device__ __forceinline__ bool pml_jacobi_cell_of(PmlCell& c, int rep, int bx,
+                                                   int by, int bz) {
 #if PML_NDIM <= 1
-  (void)rep;
-  return pml_this_cell(c);
+  (void)rep; (void)by; (void)bz;
+  c.i0 = bx * PML_BX + threadIdx.x;
+  c.i1 = 0;
+  c.i2 = 0;
+  c.idx = c.i0;
+  return c.i0 < PML_N0;
 #elif PML_NDIM == 2
-  c.i1 = blockIdx.x * PML_BX + threadIdx.x;
-  c.i0 = (blockIdx.y * PML_JREP + rep) * PML_BY + threadIdx.y;
+  (void)bz;
+  c.i1 = bx * PML_BX + threadIdx.x;
+  c.i0 = (by * PML_JREP + rep) * PML_BY + threadIdx.y;
   c.i2 = 0;
   c.idx = pml_lin(c.i0, c.i1, 0);
   return c.i1 < PML_N1 && c.i0 < PML_N0;
 #else
-  c.i2 = blockIdx.x * PML_BX + threadIdx.x;
-  c.i1 = blockIdx.y * PML_BY + threadIdx.y;
-  c.i0 = (blockIdx.z * PML_JREP + rep) * PML_BZ + threadIdx.z;
+  c.i2 = bx * PML_BX + threadIdx.x;
+  c.i1 = by * PML_BY + threadIdx.y;
+  c.i0 = (bz * PML_JREP + rep) * PML_BZ + threadIdx.z;
   c.idx = pml_lin(c.i0, c.i1, c.i2);
   return c.i2 < PML_N2 && c.i1 < PML_N1 && c.i0 < PML_N0;
 #endif
 }
+__device__ __forceinline__ bool pml_jacobi_cell(PmlCell& c, int rep) {
+  return pml_jacobi_cell_of(c, rep, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+// one plane read with ordinary (coherent) loads: the persistent Jacobi loop
+// re-reads planes other thread blocks wrote earlier in the same launch, which
+// the read-only path of PmlPlaneSrc must not be used for
+struct PmlPlaneSrcCoherent {
+  const double* p;
+  template <int D0, int D1, int D2>
+  __device__ __forceinline__ double rel(int, const PmlCell& c) const {
+    constexpr i64 off = D0 * PmlAx<0>::S + D1 * PmlAx<1>::S + D2 * PmlAx<2>::S;
+    return p[c.idx + off];
+  }
+};
 
 // one Jacobi update of one cell; IM as in the stencil primitives (interior
 // warps run without any boundary handling)
-template <int IM>
+template <int IM, class PLANE = PmlPlaneSrc>
 __device__ __forceinline__ double pml_jacobi_cell_update(const PmlJacobiArgs& j,
                                                          const PmlCell& c) {
   const PmlArgs& a = j.base;
@@ -1794,7 +1819,7 @@ __device__ __forceinline__ double pml_jacobi_cell_update(const PmlJacobiArgs& j,
   for (int q = 0; q < PML_NLAP; ++q) {
     const int comp = PML_LAP_IDX[q];
     const double* p = j.y_hat + (i64)q * PML_NCELLS;
-    const PmlPlaneSrc ps{p};
+    const PLANE ps{p};
     double lo, hi, acc = 0.0;
 #if PML_COORD == 0
     pml_nb2<0, IM>(a, ps, comp, c, lo, hi);
@@ -1841,7 +1866,7 @@ __device__ __forceinline__ double pml_jacobi_cell_update(const PmlJacobiArgs& j,
 #endif
     const double vn = pml_dirichlet(a.dir, comp, c, v);
     j.y_new[(i64)q * PML_NCELLS + c.idx] = vn;
-    const double d = vn - PML_LD(p + c.idx);
+    const double d = vn - ps.template rel<0, 0, 0>(comp, c);
     sq += d * d;
   }
   return sq;
@@ -1901,6 +1926,92 @@ extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ)
     j.flags[1] += 1;
     j.flags[2] = 0;
     if (!(sqrt(lanes[0]) > j.tol)) j.flags[0] = 1;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// The whole Jacobi iteration in ONE cooperative launch: a persistent grid (as
+// many thread blocks as are resident at once) walks the tiles of the sweep
+// kernel above, sweep after sweep, with a grid-wide barrier in between; every
+// block then adds up the per-block partial sums of the update norm in the same
+// fixed order, so all blocks take the same decision to stop
+// (numerical_differentiator.py:917-925) without another barrier or a round
+// trip to the host.  flags[3] is the barrier counter (zeroed by the host).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void pml_grid_barrier(unsigned* counter, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) {
+    unsigned seen;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];"
+                   : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < target);
+  }
+  __syncthreads();
+}
+
+extern "C" __global__ void __launch_bounds__(PML_BX* PML_BY* PML_BZ)
+    pml_jacobi_loop(const __grid_constant__ PmlJacobiArgs j0, int max_sweeps,
+                    int gx, int gy, int gz) {
+  PmlJacobiArgs j = j0;
+  constexpr int NT = PML_BX * PML_BY * PML_BZ;
+  const int tid = (threadIdx.z * PML_BY + threadIdx.y) * PML_BX + threadIdx.x;
+  const int n_tiles = gx * gy * gz;
+  const int n_blocks = (int)gridDim.x;
+  unsigned* barrier = (unsigned*)(j.flags + 3);
+  __shared__ double red[32];
+  __shared__ double lanes[256];
+  int sweeps = 0, done = 0;
+  while (!done && (max_sweeps <= 0 || sweeps < max_sweeps)) {
+    double sq = 0.0;
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < n_tiles; tile += n_blocks) {
+      const int bx = tile % gx, by = (tile / gx) % gy, bz = tile / (gx * gy);
+#pragma unroll
+      for (int rep = 0; rep < (PML_NDIM <= 1 ? 1 : PML_JREP); ++rep) {
+        PmlCell c;
+        const bool active = pml_jacobi_cell_of(c, rep, bx, by, bz);
+        const int path = pml_warp_path(active, c);
+        if (active)
+          sq += path == 2
+                    ? pml_jacobi_cell_update<PML_IM_ALL, PmlPlaneSrcCoherent>(j, c)
+                    : pml_jacobi_cell_update<0, PmlPlaneSrcCoherent>(j, c);
+      }
+    }
+    // deterministic block reduction, one partial per block and sweep parity
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sq += __shfl_down_sync(0xffffffffu, sq, off);
+    if ((tid & 31) == 0) red[tid >> 5] = sq;
+    __syncthreads();
+    double* partials = j.partials + (sweeps & 1) * n_blocks;
+    if (tid == 0) {
+      double s = 0.0;
+      for (int w = 0; w < (NT + 31) / 32; ++w) s += red[w];
+      partials[blockIdx.x] = s;
+    }
+    ++sweeps;
+    pml_grid_barrier(barrier, (unsigned)sweeps * (unsigned)n_blocks);
+    // the norm of this sweep's update, summed identically by every block
+    for (int v = tid; v < 256; v += NT) {
+      double s = 0.0;
+      for (int i = v; i < n_blocks; i += 256) s += __ldcg(partials + i);
+      lanes[v] = s;
+    }
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+      for (int v = tid; v < off; v += NT) lanes[v] += lanes[v + off];
+      __syncthreads();
+    }
+    done = !(sqrt(lanes[0]) > j.tol);
+    __syncthreads();  // lanes / red are rewritten by the next sweep
+    const double* swap = j.y_hat;
+    j.y_hat = j.y_new;
+    j.y_new = const_cast<double*>(swap);
+  }
+  if (blockIdx.x == 0 && tid == 0) {
+    j.flags[0] = done;
+    j.flags[1] = sweeps;
   }
 }
 

@@ -50,6 +50,10 @@ struct Driver {
   CUresult (*launchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned,
                            unsigned, unsigned, unsigned, CUstream, void**,
                            void**) = nullptr;
+  CUresult (*launchCooperativeKernel)(CUfunction, unsigned, unsigned, unsigned,
+                                      unsigned, unsigned, unsigned, unsigned,
+                                      CUstream, void**) = nullptr;
+  CUresult (*occupancyMaxActiveBlocks)(int*, CUfunction, int, size_t) = nullptr;
   CUresult (*getErrorString)(CUresult, const char**) = nullptr;
   CUresult (*funcSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
   CUresult (*tensorMapEncodeTiled)(
@@ -72,6 +76,9 @@ int load_driver() {
       {"cuModuleUnload", (void**)&g_drv.moduleUnload},
       {"cuModuleGetFunction", (void**)&g_drv.moduleGetFunction},
       {"cuLaunchKernel", (void**)&g_drv.launchKernel},
+      {"cuLaunchCooperativeKernel", (void**)&g_drv.launchCooperativeKernel},
+      {"cuOccupancyMaxActiveBlocksPerMultiprocessor",
+       (void**)&g_drv.occupancyMaxActiveBlocks},
       {"cuGetErrorString", (void**)&g_drv.getErrorString},
       {"cuFuncSetAttribute", (void**)&g_drv.funcSetAttribute},
       {"cuTensorMapEncodeTiled", (void**)&g_drv.tensorMapEncodeTiled},
@@ -127,6 +134,7 @@ struct PmlFusedArgs {
   double t_eval_b;
   const double* neu_b[6];
   const double* dir_b[6];
+  int z_begin, z_end;
 };
 
 struct PmlSmallArgs {
@@ -221,6 +229,8 @@ struct pml_plan {
   CUfunction eval_rhs = nullptr;
   CUfunction apply_dir = nullptr;
   CUfunction jac_init = nullptr, jac_sweep = nullptr, jac_store = nullptr;
+  CUfunction jac_loop = nullptr;  // persistent cooperative form of the sweeps
+  int jac_loop_blocks = 0;        // thread blocks resident at once
   pml_tables tables{};
   dim3 grid, block;
   dim3 sgrid;  // grid of the stage kernels (zrep cells along axis 0 per thread)
@@ -284,7 +294,7 @@ int jacobi_solve(pml_plan* p, const pml_workspace* ws, const PmlArgs& tbl,
                  double tol, long long max_sweeps, int* sweeps_out,
                  CUstream s) {
   // tbl carries the slots of t + dt for both Neumann and Dirichlet tables
-  PML_CUDA(cudaMemsetAsync(ws->flags, 0, 3 * sizeof(int), (cudaStream_t)s));
+  PML_CUDA(cudaMemsetAsync(ws->flags, 0, 4 * sizeof(int), (cudaStream_t)s));
   {
     PmlArgs a = tbl;
     const double* init = y_init;
@@ -293,8 +303,48 @@ int jacobi_solve(pml_plan* p, const pml_workspace* ws, const PmlArgs& tbl,
     if (launch(p, p->jac_init, params, s)) return -1;
   }
   double* bufs[2] = {ws->jac_a, ws->jac_b};
-  long long issued = 0;
   int host_flags[2] = {0, 0};
+  // all sweeps and their convergence tests in one cooperative launch of a
+  // persistent grid (PML_JACOBI_LOOP=0: one launch per sweep, in batches
+  // between which the host reads the convergence flag)
+  static const bool use_loop = [] {
+    const char* e = std::getenv("PML_JACOBI_LOOP");
+    return !(e && e[0] == '0');
+  }();
+  if (use_loop) {
+    if (p->jac_loop_blocks == 0) {
+      int per_sm = 0, sms = 0, dev = 0;
+      PML_CUDA(cudaGetDevice(&dev));
+      PML_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      PML_CU(g_drv.occupancyMaxActiveBlocks(
+          &per_sm, p->jac_loop, (int)(p->block.x * p->block.y * p->block.z), 0));
+      if (per_sm < 1) return fail("the Jacobi loop kernel does not fit an SM");
+      p->jac_loop_blocks = per_sm * sms;
+    }
+    const long long tiles = (long long)p->jgrid.x * p->jgrid.y * p->jgrid.z;
+    // two partial sums per block (sweep parity) live in ws->partials
+    long long blocks = std::min<long long>(tiles, p->jac_loop_blocks);
+    blocks = std::min<long long>(blocks, std::max<long long>(p->n_blocks / 2, 1));
+    PmlJacobiArgs j;
+    j.base = tbl;
+    j.y_hat = bufs[0];
+    j.rhs = rhs;
+    j.y_new = bufs[1];
+    j.partials = ws->partials;
+    j.flags = ws->flags;
+    j.tol = tol;
+    int cap = max_sweeps > 0x7fffffffLL ? 0x7fffffff : (int)max_sweeps;
+    int gx = (int)p->jgrid.x, gy = (int)p->jgrid.y, gz = (int)p->jgrid.z;
+    void* params[] = {&j, &cap, &gx, &gy, &gz};
+    PML_CU(g_drv.launchCooperativeKernel(p->jac_loop, (unsigned)blocks, 1, 1,
+                                         p->block.x, p->block.y, p->block.z, 0, s,
+                                         params));
+    p->launches += 1;
+    PML_CUDA(cudaMemcpyAsync(host_flags, ws->flags, 2 * sizeof(int),
+                             cudaMemcpyDeviceToHost, (cudaStream_t)s));
+    PML_CUDA(cudaStreamSynchronize((cudaStream_t)s));
+  } else {
+  long long issued = 0;
   // sweeps are enqueued in growing batches; after each batch the host reads
   // the convergence flag (launches after convergence return at once)
   long long batch = 32;
@@ -323,6 +373,7 @@ int jacobi_solve(pml_plan* p, const pml_workspace* ws, const PmlArgs& tbl,
     if (host_flags[0]) break;
     if (batch < 8192) batch *= 2;
   }
+  }
   const long long sweeps = host_flags[1];
   if (sweeps_out) *sweeps_out = (int)sweeps;
   const double* result = bufs[sweeps & 1];
@@ -336,7 +387,14 @@ int jacobi_solve(pml_plan* p, const pml_workspace* ws, const PmlArgs& tbl,
 // last phase (a domain-decomposed caller exchanges its halo planes then).
 int run_step(pml_plan* p, int integrator, const pml_workspace* ws, PmlArgs& a,
              const double* y, double* y_next, double t, double d_t,
-             long long s_t, int phase, double** fresh, CUstream s) {
+             long long s_t, int phase, double** fresh, CUstream s,
+             int z_begin = 0, int z_end = -1) {
+  // planes [z_begin, z_end) of axis 0 (stage-pair kernels only); default: all
+  const int n_planes = p->desc.shape[0];
+  if (z_end < 0) z_end = n_planes;
+  const bool whole = z_begin == 0 && z_end == n_planes;
+  if (z_begin < 0 || z_end > n_planes || z_begin >= z_end)
+    return fail("plane range out of bounds");
   const double half = d_t / 2.0;
   const long long s_h = s_t + 1, s_f = s_t + 2;
   a.y = y;
@@ -394,9 +452,16 @@ int run_step(pml_plan* p, int integrator, const pml_workspace* ws, PmlArgs& a,
     f.t_eval_b = t_b;
     bind_neu(p, f.neu_b, neu_b);
     bind_dir(p, f.dir_b, dir_b);
+    f.z_begin = z_begin;
+    f.z_end = z_end;
+    // the chunks of the marching axis are the last used grid dimension
+    const unsigned chunks =
+        (unsigned)((z_end - z_begin + p->desc.fused_zc - 1) / p->desc.fused_zc);
+    dim3 grid = p->fgrid;
+    if (p->desc.n_dims == 3) grid.z = chunks; else grid.y = chunks;
     void* fparams[] = {&f};
-    CUresult r_ = g_drv.launchKernel(p->fused[k], p->fgrid.x, p->fgrid.y,
-                                     p->fgrid.z, p->fblock.x, p->fblock.y, 1,
+    CUresult r_ = g_drv.launchKernel(p->fused[k], grid.x, grid.y,
+                                     grid.z, p->fblock.x, p->fblock.y, 1,
                                      p->fsmem[k], s, fparams, nullptr);
     if (r_ != CUDA_SUCCESS) return fail("fused launch: " + cu_err(r_));
     p->launches += 1;
@@ -412,6 +477,8 @@ int run_step(pml_plan* p, int integrator, const pml_workspace* ws, PmlArgs& a,
   if (p->desc.fused && phase >= 0 && !all_aligned)
     return fail("phase-wise stepping needs 16-byte aligned states");
   const bool use_fused = p->desc.fused && all_aligned;
+  if (!whole && (!use_fused || integrator == PML_INTEGRATOR_FORWARD_EULER))
+    return fail("plane ranges need the stage-pair kernels");
   if (integrator == PML_INTEGRATOR_FORWARD_EULER) {
     rc = stage(0, y, nullptr, t, s_t, s_f);
   } else if (use_fused && integrator == PML_INTEGRATOR_EXPLICIT_MIDPOINT) {
@@ -547,7 +614,7 @@ int pml_plan_create(const char* source, const pml_plan_desc* desc,
   if (desc->n_lap > 0) {
     struct { const char* n; CUfunction* f; } js[] = {
         {"pml_jacobi_init", &p->jac_init}, {"pml_jacobi_sweep", &p->jac_sweep},
-        {"pml_jacobi_store", &p->jac_store}};
+        {"pml_jacobi_store", &p->jac_store}, {"pml_jacobi_loop", &p->jac_loop}};
     for (auto& j : js) {
       r = g_drv.moduleGetFunction(j.f, p->module, j.n);
       if (r != CUDA_SUCCESS) {
@@ -727,6 +794,14 @@ int pml_fdm_phase_count(const pml_plan* p, int integrator) {
 int pml_fdm_phase(pml_plan* p, int integrator, const pml_workspace* ws,
                   const double* y, double* y_next, double t, double d_t,
                   long long slot0, int phase, double** fresh_out, void* stream) {
+  return pml_fdm_phase_planes(p, integrator, ws, y, y_next, t, d_t, slot0, phase,
+                              0, -1, fresh_out, stream);
+}
+
+int pml_fdm_phase_planes(pml_plan* p, int integrator, const pml_workspace* ws,
+                         const double* y, double* y_next, double t, double d_t,
+                         long long slot0, int phase, int z_begin, int z_end,
+                         double** fresh_out, void* stream) {
   if (!p || !ws || !y || !y_next) return fail("null argument");
   if (integrator < 0 || integrator > 2) return fail("unknown integrator");
   if (p->desc.n_lap > 0 || p->desc.n_alg > 0)
@@ -739,7 +814,7 @@ int pml_fdm_phase(pml_plan* p, int integrator, const pml_workspace* ws,
   a.dt = d_t;
   a.lap_rhs = ws->lap_rhs;
   return run_step(p, integrator, ws, a, y, y_next, t, d_t, slot0, phase,
-                  fresh_out, (CUstream)stream);
+                  fresh_out, (CUstream)stream, z_begin, z_end);
 }
 
 int pml_eval_rhs(pml_plan* p, const double* u, double* out, double t,

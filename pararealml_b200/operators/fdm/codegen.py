@@ -685,6 +685,7 @@ def generate_source(spec: ProblemSpec) -> str:
         f"#define PML_FMIN_BLOCKS {fused.min_blocks if fused else 1}",
         f"#define PML_FROWS {fused.rows if fused else 1}",
         f"#define PML_FSYNC {fused.sync if fused else 0}",
+        f"#define PML_F_PATH1 {int(os.environ.get('PML_FPATH1', '1'))}",
         f"#define PML_ZREP {max(1, int(spec.zrep))}",
         f"#define PML_JREP {JACOBI_REP}",
         f"#define PML_BX {block[0]}",

@@ -171,7 +171,7 @@ class DevicePlan:
                 "u_a": torch.empty(n, **f64),
                 "u_b": torch.empty(n, **f64),
                 "acc": torch.empty(n, **f64),
-                "partials": torch.empty(max(self.n_blocks, 1), **f64),
+                "partials": torch.empty(max(self.n_blocks, 2), **f64),
                 "flags": torch.zeros(4, dtype=torch.int32, device=self.device),
             }
             nl = max(self.n_lap, 0) * self.n_cells

@@ -30,6 +30,8 @@ from pararealml_b200.operators.fdm.lowering import LoweredProblem
 
 #: halo planes per side: a fused stage pair spoils two planes from a local face
 HALO = 2
+#: planes next to a neighbouring slab that are computed ahead of the rest
+EDGE_PLANES = 8
 
 
 def slab_bounds(n_planes: int, size: int, rank: int) -> Tuple[int, int]:
@@ -143,6 +145,7 @@ class SlabSolver:
         self._pack = [torch.empty(n_send, **f64) for _ in range(2)]
         self._unpack = [torch.empty(n_send, **f64) for _ in range(2)]
         self._ops = None  # NCCL: the four transfers, built once
+        self._comm = None  # side stream of the overlapped halo exchange
 
     # -- layout ---------------------------------------------------------------
     def local_planes(self, y: np.ndarray) -> torch.Tensor:
@@ -210,28 +213,74 @@ class SlabSolver:
             halo_view.copy_(recv.view(shape).to(buf.device))
 
     # -- time stepping ----------------------------------------------------------
+    def _launch(self, y, y_next, t, d_t, phase, z_begin, z_end, fresh):
+        _native.check(
+            _native.lib().pml_fdm_phase_planes(
+                self.plan.handle, self.code, ctypes.byref(self._ws),
+                y.data_ptr(), y_next.data_ptr(), float(t), float(d_t),
+                0, phase, z_begin, z_end, ctypes.byref(fresh), dv.stream_ptr(),
+            )
+        )
+
+    def edge_ranges(self):
+        """Plane ranges of one phase: the planes next to a neighbouring slab
+        (launched first, their outermost owned planes are what the neighbour
+        waits for) and the remaining planes, whose launch the halo exchange
+        overlaps.  Without the stage-pair kernels, or on slabs too thin to
+        split, one launch covers everything."""
+        n = self.n_loc
+        edge = min(EDGE_PLANES, n // 4)
+        # (forward Euler is a single stage: it has no stage-pair kernel)
+        if (not self.plan.spec.fused or self.family == "forward_euler"
+                or self.size == 1 or edge < 2 * HALO):
+            return [], (0, n)
+        edges = []
+        lo, hi = 0, n
+        if self.rank > 0:
+            edges.append((0, edge))
+            lo = edge
+        if self.rank + 1 < self.size:
+            edges.append((n - edge, n))
+            hi = n - edge
+        return edges, (lo, hi)
+
     def integrate(self, y0_planes: torch.Tensor, t: np.ndarray, d_t: float,
                   traj: torch.Tensor):
         """Steps starting at ``t[:-1]`` from the local planes ``y0_planes``
         (halo planes valid) into ``traj[j]`` (local planes, halo planes valid
-        on return)."""
-        lib = _native.lib()
+        on return).  Per launch ("phase") the planes next to the neighbours
+        are computed first; their exchange (side stream) runs while the rest
+        of the slab is computed."""
         n_steps = len(t) - 1
         assert traj.shape == (n_steps, self.state) and traj.is_contiguous()
         fresh = ctypes.c_void_p()
+        edges, rest = self.edge_ranges()
+        overlap = bool(edges) and self.on_nccl
+        compute = torch.cuda.current_stream()
+        if overlap and self._comm is None:
+            self._comm = torch.cuda.Stream()
         y = y0_planes
         for j in range(n_steps):
             y_next = traj[j]
             for phase in range(self.n_phases):
-                _native.check(
-                    lib.pml_fdm_phase(
-                        self.plan.handle, self.code, ctypes.byref(self._ws),
-                        y.data_ptr(), y_next.data_ptr(), float(t[j]), float(d_t),
-                        0, phase, ctypes.byref(fresh), dv.stream_ptr(),
-                    )
-                )
+                for z_begin, z_end in edges:
+                    self._launch(y, y_next, t[j], d_t, phase, z_begin, z_end, fresh)
+                if overlap:
+                    ready = torch.cuda.Event()
+                    ready.record(compute)
+                self._launch(y, y_next, t[j], d_t, phase, rest[0], rest[1], fresh)
                 buf = y_next if fresh.value == y_next.data_ptr() else self._ws_by_ptr[fresh.value]
-                self.exchange(buf[: self.state])
+                if overlap:
+                    # the edge planes are final: exchange them on the side
+                    # stream while the launch above computes the interior
+                    with torch.cuda.stream(self._comm):
+                        self._comm.wait_event(ready)
+                        self.exchange(buf[: self.state])
+                        done = torch.cuda.Event()
+                        done.record(self._comm)
+                    compute.wait_event(done)
+                else:
+                    self.exchange(buf[: self.state])
             y = y_next
 
     # -- gathering ----------------------------------------------------------------

@@ -127,6 +127,9 @@ class Solution:
         """Differences to other solutions at the time points all share."""
         if len(solutions) == 0:
             raise ValueError("at least one solution to compare to is needed")
+        on_device = self._device_diff(solutions, atol)
+        if on_device is not None:
+            return on_device
         mine = self._materialise()
         others = [s.discrete_y(self._vertex_oriented) for s in solutions]
         grids = [self._t] + [s.t_coordinates for s in solutions]
@@ -151,6 +154,82 @@ class Solution:
             for j, other in enumerate(others):
                 diffs[j].append(other[where[j + 1]] - mine[where[0]])
         return Diffs(np.array(matched), [np.array(d) for d in diffs])
+
+    def _matching_indices(self, solutions, atol):
+        """(matched times, per solution (self first) the index of every
+        matched time point) -- the time-point matching rule of ``diff``."""
+        grids = [self._t] + [s.t_coordinates for s in solutions]
+        steps = [self._d_t] + [s.d_t for s in solutions]
+        shortest = int(np.argmin([len(g) for g in grids]))
+        matched: List[float] = []
+        indices: List[List[int]] = [[] for _ in grids]
+        for i, t in enumerate(grids[shortest]):
+            where = []
+            for j, g in enumerate(grids):
+                if j == shortest:
+                    where.append(i)
+                    continue
+                k = int(round((t - g[0]) / steps[j]))
+                if 0 <= k < len(g) and np.isclose(t, g[k], atol=atol, rtol=0.0):
+                    where.append(k)
+                else:
+                    break
+            if len(where) != len(grids):
+                continue
+            matched.append(t)
+            for j, k in enumerate(where):
+                indices[j].append(k)
+        return np.array(matched), indices
+
+    def _device_diff(self, solutions, atol):
+        """``diff`` for trajectories that are still resident in HBM (lazy
+        solutions of ``FDMOperator.device_resident_solution``): the matching
+        steps are subtracted on the device and only the differences cross
+        PCIe.  None if any solution has already been copied to the host."""
+        everyone = [self] + list(solutions)
+        if any(
+            getattr(s, "device_trajectory", None) is None
+            or getattr(s, "_y", None) is not None
+            or s.vertex_oriented != self._vertex_oriented
+            or s.device_trajectory.shape[1] != self.device_trajectory.shape[1]
+            for s in everyone
+        ):
+            return None
+        import torch
+
+        from pararealml_b200 import _native
+        from pararealml_b200.operators.fdm import device as dv
+
+        matched, indices = self._matching_indices(solutions, atol)
+        mine = self.device_trajectory
+        state = mine.shape[1]
+        y_dim = self._expected_shape[-1]
+        n_cells = state // y_dim
+        lib = _native.lib()
+        out = []
+        for j, other in enumerate(solutions):
+            planes = torch.empty(
+                (len(matched), state), dtype=torch.float64, device=mine.device
+            )
+            for row, (k_other, k_mine) in enumerate(zip(indices[j + 1], indices[0])):
+                # other - mine (the subtraction kernel of the Parareal
+                # correction: a - b over one state)
+                _native.check(
+                    lib.pml_parareal_correction(
+                        other.device_trajectory[k_other].data_ptr(),
+                        mine[k_mine].data_ptr(), planes[row].data_ptr(),
+                        state, dv.stream_ptr(),
+                    )
+                )
+            host = torch.empty(planes.shape, dtype=torch.float64, pin_memory=True)
+            if len(matched):
+                aos = dv.soa_to_aos(planes, n_cells, y_dim, len(matched))
+                host.copy_(aos, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+            out.append(
+                host.numpy().reshape((len(matched),) + self._expected_shape[1:])
+            )
+        return Diffs(matched, out)
 
     def generate_plots(self, **kwargs):
         raise NotImplementedError(

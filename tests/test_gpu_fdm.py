@@ -155,6 +155,37 @@ def test_device_resident_solution_is_read_lazily():
     assert per_step_rel_err(sol.discrete_y()[g["steps"]], g["y"]) <= 1e-12
 
 
+def test_diff_of_device_resident_solutions_stays_on_the_device():
+    """Solution.diff (reference solution.py:182-262) between lazy solutions
+    subtracts the matching steps in HBM; only the differences are copied."""
+    case = cases.FDM_BY_NAME["shallow_water_polar_rk4"]
+    ivp = case.build(ns)
+    ops = []
+    for ratio in (1, 2, 5):
+        op = FDMOperator(
+            INTEGRATORS[case.integrator](),
+            ThreePointCentralDifferenceMethod(case.tol), case.d_t * ratio,
+        )
+        ops.append(op)
+    eager = [op.solve(ivp) for op in ops]
+    expected = eager[0].diff(eager[1:])
+    for op in ops:
+        op.device_resident_solution = True
+    lazy = [op.solve(ivp) for op in ops]
+    got = lazy[0].diff(lazy[1:])
+    assert all(s._y is None for s in lazy)  # nothing was materialised
+    assert np.array_equal(got.matching_time_points, expected.matching_time_points)
+    assert len(got.matching_time_points) == 1  # t = 0.025 only
+    assert np.isfinite(expected.differences[1]).all()
+    for a, b in zip(got.differences, expected.differences):
+        assert a.shape == b.shape and np.array_equal(a, b)
+    # a solution that has been read falls back to the host arrays
+    lazy[1].discrete_y()
+    again = lazy[0].diff(lazy[1:])
+    for a, b in zip(again.differences, expected.differences):
+        assert np.array_equal(a, b)
+
+
 @pytest.mark.parametrize(
     "case_name",
     ["diffusion_2d_rk4", "wave_2d_dynamic_mid", "cahn_hilliard_3d_rk4",
