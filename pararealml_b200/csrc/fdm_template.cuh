@@ -638,7 +638,9 @@ struct PmlRingSrc {
   }
 };
 
-enum { PML_F_RK4_12 = 0, PML_F_RK4_34 = 1, PML_F_MID = 2 };
+// PML_F_FE2: two consecutive forward Euler steps (marching variant only): stage
+// A is step j (written to u_out as well), stage B step j + 1
+enum { PML_F_RK4_12 = 0, PML_F_RK4_34 = 1, PML_F_MID = 2, PML_F_FE2 = 3 };
 
 __device__ __forceinline__ unsigned pml_smem_addr(const void* p) {
   return (unsigned)__cvta_generic_to_shared(p);
@@ -1396,6 +1398,8 @@ struct PmlMarch {
       double ua, kk = 0.0;
       if (MODE == PML_F_MID) {
         ua = y0 + (a.dt / 2.0) * K[j];
+      } else if (MODE == PML_F_FE2) {
+        ua = y0 + a.dt * K[j];
       } else {
         kk = a.dt * K[j];
         ua = MODE == PML_F_RK4_12 ? y0 + kk / 2.0 : y0 + kk;
@@ -1403,7 +1407,13 @@ struct PmlMarch {
       const double v = pml_dirichlet(a.dir, k, c, ua);
       mid_col[ROW][pml_ring_index(k)][PH % 3] = v;
       pm[pml_ring_index(k) * PML_MID_PLANE + ROW * PML_MW] = v;
-      ka[ROW][j][(PH + 1) % 3] = kk;
+      if (MODE == PML_F_FE2) {
+        // the first of the two steps is a result as well
+        if (((own_mask >> ROW) & 1u) && p >= zb && p < ze)
+          PML_ST(a.u_out + (i64)k * PML_NCELLS + c.idx, v);
+      } else {
+        ka[ROW][j][(PH + 1) % 3] = kk;
+      }
     }
 #if PML_NALG + PML_NLAP > 0
     if (!PML_PASSTHROUGH) {
@@ -1452,8 +1462,11 @@ struct PmlMarch {
       const i64 o = (i64)k * PML_NCELLS + c.idx;
       // the step-start value: stages 1+2 / midpoint re-read it from the input
       // ring (plane i - 1 is still there), stages 3+4 from the y ring
-      const double y0 = first ? py[pml_ring_index(k) * PML_IN_PLANE + ROW * PML_IW]
-                              : py[j * PML_YR_PLANE + ROW * PML_IW];
+      // (two Euler steps: the second starts from stage A's own result)
+      const double y0 = MODE == PML_F_FE2
+                            ? mid_col[ROW][pml_ring_index(k)][(PH + 1) % 3]
+                            : (first ? py[pml_ring_index(k) * PML_IN_PLANE + ROW * PML_IW]
+                                     : py[j * PML_YR_PLANE + ROW * PML_IW]);
       const double k_a = ka[ROW][j][(PH + 2) % 3];
       if (MODE == PML_F_RK4_12) {
         const double kk = b.dt * K[j];
@@ -1604,6 +1617,7 @@ struct PmlMarch {
 PML_MARCH_KERNEL(pml_fused_rk4_12, PML_F_RK4_12)
 PML_MARCH_KERNEL(pml_fused_rk4_34, PML_F_RK4_34)
 PML_MARCH_KERNEL(pml_fused_mid, PML_F_MID)
+PML_MARCH_KERNEL(pml_fused_fe2, PML_F_FE2)
 #endif  // PML_FUSED == 2
 
 // ---------------------------------------------------------------------------

@@ -105,6 +105,9 @@ std::string cu_err(CUresult r) {
     if (r_ != CUDA_SUCCESS) return fail(std::string(#call) + ": " + cu_err(r_)); \
   } while (0)
 
+// internal: two forward Euler steps in one stage-pair launch
+#define PML_INTEGRATOR_FE_PAIR 100
+
 // cells along axis 0 per thread of the Jacobi sweep (codegen.py JACOBI_REP)
 #define PML_JACOBI_REP 4
 
@@ -222,9 +225,10 @@ struct pml_plan {
   pml_plan_desc desc;
   CUmodule module = nullptr;
   CUfunction stage[7] = {};
-  CUfunction fused[3] = {};  // rk4 1+2, rk4 3+4, midpoint 1+2
+  // rk4 1+2, rk4 3+4, midpoint 1+2, two forward Euler steps (optional)
+  CUfunction fused[4] = {};
   dim3 fgrid, fblock;
-  unsigned fsmem[3] = {0, 0, 0};
+  unsigned fsmem[4] = {0, 0, 0, 0};
   CUfunction small_run = nullptr;
   CUfunction eval_rhs = nullptr;
   CUfunction apply_dir = nullptr;
@@ -388,7 +392,8 @@ int jacobi_solve(pml_plan* p, const pml_workspace* ws, const PmlArgs& tbl,
 int run_step(pml_plan* p, int integrator, const pml_workspace* ws, PmlArgs& a,
              const double* y, double* y_next, double t, double d_t,
              long long s_t, int phase, double** fresh, CUstream s,
-             int z_begin = 0, int z_end = -1) {
+             int z_begin = 0, int z_end = -1, double* y_mid = nullptr,
+             double t_next = 0.0) {
   // planes [z_begin, z_end) of axis 0 (stage-pair kernels only); default: all
   const int n_planes = p->desc.shape[0];
   if (z_end < 0) z_end = n_planes;
@@ -479,7 +484,12 @@ int run_step(pml_plan* p, int integrator, const pml_workspace* ws, PmlArgs& a,
   const bool use_fused = p->desc.fused && all_aligned;
   if (!whole && (!use_fused || integrator == PML_INTEGRATOR_FORWARD_EULER))
     return fail("plane ranges need the stage-pair kernels");
-  if (integrator == PML_INTEGRATOR_FORWARD_EULER) {
+  if (integrator == PML_INTEGRATOR_FE_PAIR) {
+    // two forward Euler steps: y -> y_mid (step starting at t) -> y_next
+    // (step starting at t + d_t; its table slots follow three later)
+    if (!use_fused || !p->fused[3] || !y_mid) return fail("no Euler pair kernel");
+    rc = fused(3, y, y_mid, t, s_t, s_f, t_next, s_t + 3, s_t + 5);
+  } else if (integrator == PML_INTEGRATOR_FORWARD_EULER) {
     rc = stage(0, y, nullptr, t, s_t, s_f);
   } else if (use_fused && integrator == PML_INTEGRATOR_EXPLICIT_MIDPOINT) {
     rc = fused(2, y, nullptr, t, s_t, s_h, t + half, s_h, s_f);
@@ -568,6 +578,22 @@ int pml_plan_create(const char* source, const pml_plan_desc* desc,
     p->fsmem[0] = (unsigned)desc->fused_smem[0];
     p->fsmem[1] = (unsigned)desc->fused_smem[1];
     p->fsmem[2] = (unsigned)desc->fused_smem[0];
+    // two forward Euler steps per launch: column-marching variant only
+    if (g_drv.moduleGetFunction(&p->fused[3], p->module, "pml_fused_fe2") ==
+        CUDA_SUCCESS) {
+      p->fsmem[3] = p->fsmem[0];
+      CUresult q = CUDA_SUCCESS;
+      if (p->fsmem[3] > 40 * 1024)
+        q = g_drv.funcSetAttribute(p->fused[3],
+                                   CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                                   (int)p->fsmem[3]);
+      if (q == CUDA_SUCCESS)
+        q = g_drv.funcSetAttribute(
+            p->fused[3], CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, 100);
+      if (q != CUDA_SUCCESS) p->fused[3] = nullptr;
+    } else {
+      p->fused[3] = nullptr;
+    }
     for (int i = 0; i < 3; ++i) {
       r = g_drv.moduleGetFunction(&p->fused[i], p->module, fnames[i]);
       if (r == CUDA_SUCCESS && p->fsmem[i] > 40 * 1024)  // static + dynamic > 48 KB needs the opt-in
@@ -762,11 +788,24 @@ static int fdm_run_batch(pml_plan* p, int integrator, const pml_workspace* ws,
                       n_steps, d_t, slot0, nullptr, 0.0, 0, nullptr, stream))
       return -1;
   }
+  auto aligned16 = [](const void* q) { return ((uintptr_t)q & 15u) == 0; };
   for (int j = 0; j < n_steps; ++j) {
     const double t = t_host[j];
     const double* y = j == 0 ? y0 : traj + (long long)(j - 1) * stride;
     double* y_next = traj + (long long)j * stride;
     const long long s_t = slot0 + 3LL * j, s_f = s_t + 2;
+    if (integrator == PML_INTEGRATOR_FORWARD_EULER && p->desc.fused &&
+        p->fused[3] && j + 1 < n_steps && p->desc.n_alg == 0 &&
+        p->desc.n_lap == 0 &&
+        aligned16(y) && aligned16(y_next) && aligned16(y_next + stride) &&
+        aligned16(ws->u_b) && aligned16(ws->acc)) {
+      // steps j and j + 1 in one launch of the stage-pair kernel
+      if (run_step(p, PML_INTEGRATOR_FE_PAIR, ws, a, y, y_next + stride, t, d_t,
+                   s_t, -1, nullptr, s, 0, -1, y_next, t_host[j + 1]))
+        return -1;
+      ++j;
+      continue;
+    }
     if (run_step(p, integrator, ws, a, y, y_next, t, d_t, s_t, -1, nullptr, s))
       return -1;
     if (p->desc.n_lap > 0) {

@@ -86,6 +86,23 @@ def slab_lowered(low: LoweredProblem, lo: int, hi: int) -> LoweredProblem:
     return sub
 
 
+_HALO_GROUPS = {}
+
+
+def _halo_group():
+    """A second NCCL communicator over all ranks whose kernels run on a
+    high-priority stream (made once, kept for reuse)."""
+    key = None
+    if key not in _HALO_GROUPS:
+        ranks = list(range(dist.get_world_size()))
+        try:
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            _HALO_GROUPS[key] = dist.new_group(ranks, backend="nccl", pg_options=opts)
+        except (AttributeError, TypeError):  # option not available: plain group
+            _HALO_GROUPS[key] = dist.new_group(ranks, backend="nccl")
+    return _HALO_GROUPS[key]
+
+
 class SlabSolver:
     """Per-rank state of a slab-decomposed solve of a (static boundary
     condition, fully time-stepped) problem."""
@@ -107,6 +124,12 @@ class SlabSolver:
         self.size = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.on_nccl = dist.get_backend(group) == "nccl"
+        # NCCL, all ranks of the job: the halo transfers get their own
+        # communicator on a high-priority stream (new_group is collective over
+        # the default group, so a caller-made subgroup is used as it is)
+        self.halo_group = (
+            _halo_group() if (self.on_nccl and group is None) else group
+        )
         self.low = low
         self.family = family
         n0 = low.shape[0]
@@ -192,8 +215,8 @@ class SlabSolver:
                 self._ops = []
                 for side, peer, _, _ in sides:
                     g = self._global(peer)
-                    self._ops.append(dist.P2POp(dist.isend, self._pack[side], g, self.group))
-                    self._ops.append(dist.P2POp(dist.irecv, self._unpack[side], g, self.group))
+                    self._ops.append(dist.P2POp(dist.isend, self._pack[side], g, self.halo_group))
+                    self._ops.append(dist.P2POp(dist.irecv, self._unpack[side], g, self.halo_group))
             for work in dist.batch_isend_irecv(self._ops):
                 work.wait()
             for side, _, _, halo_view in sides:
@@ -258,7 +281,10 @@ class SlabSolver:
         overlap = bool(edges) and self.on_nccl
         compute = torch.cuda.current_stream()
         if overlap and self._comm is None:
-            self._comm = torch.cuda.Stream()
+            # high priority: the pack / unpack copies (and, through the halo
+            # group below, NCCL's transfer kernels) take the first SMs the
+            # interior launch frees instead of queueing behind all its blocks
+            self._comm = torch.cuda.Stream(priority=-1)
         y = y0_planes
         for j in range(n_steps):
             y_next = traj[j]

@@ -13,6 +13,7 @@ from pararealml_b200.operators.fdm import (
     RK4,
     ExplicitMidpointMethod,
     FDMOperator,
+    ForwardEulerMethod,
     ThreePointCentralDifferenceMethod,
 )
 from pararealml_b200.operators.fdm import device as dv
@@ -192,4 +193,19 @@ def test_fused_pairs_match_stage_kernels_and_oracle(problem, integrator, monkeyp
     assert per_step_rel_err(fused, staged) <= 1e-14
     name = "rk4" if integrator is RK4 else "explicit_midpoint"
     _, y_oracle = oracle.fdm_solve(ivp, name, d_t)
+    assert per_step_rel_err(fused, y_oracle) <= 1e-12
+
+
+@pytest.mark.parametrize(
+    "problem", [p for p in PROBLEMS if p != "cahn_hilliard_3d"]
+)
+def test_euler_step_pairs_match_stage_kernels_and_oracle(problem, monkeypatch):
+    """Forward Euler: two consecutive steps per launch of the stage-pair kernel
+    (the odd last step runs the stage kernel)."""
+    ivp, d_t, fused, n_fused = solve(problem, ForwardEulerMethod, True, monkeypatch, 5)
+    _, _, staged, n_staged = solve(problem, ForwardEulerMethod, False, monkeypatch, 5)
+    assert np.isfinite(fused).all()
+    assert n_staged - n_fused == 2  # 2 pairs + 1 single against 5 launches
+    assert per_step_rel_err(fused, staged) <= 1e-14
+    _, y_oracle = oracle.fdm_solve(ivp, "forward_euler", d_t)
     assert per_step_rel_err(fused, y_oracle) <= 1e-12
