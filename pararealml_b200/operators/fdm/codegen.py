@@ -510,6 +510,9 @@ class _LeafBuilder:
     def laplacian(self, c):
         cs = self.cs
         if cs == "CARTESIAN":
+            if os.environ.get("PML_FAST_LAPLACIAN", "1") != "0":
+                # one FMA chain over the axes (fdm_template.cuh::pml_lap_at)
+                return self._prim(f"LAP_{c}", f"pml_lap_at<IM>(a, S, {c}, c)")
             return "(" + " + ".join(self.D2(c, a) for a in range(self.nd)) + ")"
         ir = self.IR()
         if cs == "SPHERICAL":
@@ -698,6 +701,8 @@ def generate_source(spec: ProblemSpec) -> str:
         lines.append(f"#define PML_INVHH{a} {c_double(1.0 / (h[a] * h[a]))}")
     inv_diag = 1.0 / float((2.0 / np.square(np.array(spec.d_x))).sum()) if nd else 1.0
     lines.append(f"#define PML_JAC_INV_DIAG {c_double(inv_diag)}")
+    lap_diag = -2.0 * float(sum(1.0 / (float(v) * float(v)) for v in spec.d_x)) if nd else 0.0
+    lines.append(f"#define PML_LAP_DIAG {c_double(lap_diag)}")
     lines.append(
         f"static __device__ constexpr int PML_KIND[] = {_int_list(kinds)};"
     )

@@ -80,7 +80,12 @@ def plan_overrides(cp, low: LoweredProblem, y0: Optional[np.ndarray],
         if sym.name.startswith("y-vector-laplacian"):
             # the reference's symbol mapper never stores this evaluator
             # (symbol_mapper.py:215-218) and fails the same way
-            raise KeyError(sym)
+            raise KeyError(
+                f"{sym}: like the reference, FDMOperator has no evaluator for "
+                "vector-Laplacian symbols (ThreePointCentralDifferenceMethod."
+                "vector_laplacian itself works; write the equation with "
+                "y-laplacian / y-gradient / y-hessian symbols instead)"
+            )
     passthrough = False
     n_other = len(low.kinds) - len(low.kind_indices("D_Y_OVER_D_T"))
     if n_other and low.all_static and low.n_dims:

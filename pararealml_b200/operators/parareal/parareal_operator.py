@@ -251,6 +251,27 @@ class PararealOperator(Operator):
         low = lowered(cp)
         return bool(low.all_static or low.n_dims == 0)
 
+    def _warn_generic_path(self, cp):
+        """Two FDM operators that still miss the device-resident path (dynamic
+        boundary conditions, a callable termination condition): say so once,
+        the host-array exchange is far slower."""
+        from pararealml_b200.operators.fdm.fdm_operator import FDMOperator
+
+        if not (isinstance(self._f, FDMOperator) and isinstance(self._g, FDMOperator)):
+            return
+        why = (
+            "a callable termination condition"
+            if callable(self._termination_condition)
+            else "dynamic boundary conditions"
+        )
+        import warnings
+
+        warnings.warn(
+            f"PararealOperator: {why} keep this solve off the device-resident "
+            "path; states are exchanged as host arrays",
+            RuntimeWarning, stacklevel=3,
+        )
+
     # ------------------------------------------------------------------
     def solve(self, ivp, parallel_enabled: bool = True) -> Solution:
         if not parallel_enabled:
@@ -263,6 +284,7 @@ class PararealOperator(Operator):
         cp = ivp.constrained_problem
         if self._device_path_available(cp, world):
             return self._solve_on_device(ivp, world)
+        self._warn_generic_path(cp)
         return self._solve_generic(ivp, world)
 
     # ------------------------------------------------------------------
