@@ -970,9 +970,6 @@ def run_b200(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # (a pod-wide NCCL_DEBUG=VERSION must not put a line in front of the
-        # JSON line on stdout)
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     builder, n_default, y_dim, dims, label = WORKLOADS[args.workload]

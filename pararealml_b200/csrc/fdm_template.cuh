@@ -193,6 +193,16 @@ __device__ __forceinline__ double pml_d1_at(const PmlArgs& a, const SRC& s,
   return pml_d1_rel<A, IM, 0, 0, 0>(a, s, comp, c);
 }
 
+// hi - lo along A at an interior cell: the first derivative times 2 h (the
+// all-interior instantiation of the generated right-hand sides multiplies the
+// mesh constant into whatever the derivative is multiplied by)
+template <int A, class SRC>
+__device__ __forceinline__ double pml_d1raw_at(const SRC& s, int comp,
+                                               const PmlCell& c) {
+  constexpr int e0 = A == 0, e1 = A == 1, e2 = A == 2;
+  return s.template rel<e0, e1, e2>(comp, c) - s.template rel<-e0, -e1, -e2>(comp, c);
+}
+
 // neighbour pair of c along A with the second-difference ghost rule:
 // ghost = inner neighbour -/+ 2 h g where a Neumann value g exists, else 0
 template <int A, int IM, class SRC>

@@ -11,6 +11,7 @@ lambdified to NumPy.
 """
 import hashlib
 import os
+import re
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -597,28 +598,75 @@ class _LeafBuilder:
         raise KeyError(name)
 
 
-def _emit_function(fn_name: str, spec: ProblemSpec, eq_indices: Sequence[int]):
+def _emit_body(spec: ProblemSpec, exprs, fold_first_derivatives: bool) -> str:
+    """Statements that evaluate ``exprs`` into ``out[]``.  With
+    ``fold_first_derivatives`` (only valid where no boundary handling applies)
+    a leaf that is a plain first derivative ``(hi - lo) / (2 h)`` enters the
+    expressions as the product of the mesh constant and the raw difference,
+    and SymPy's common-subexpression pass then shares products such as
+    ``u_a / (2 h_a)`` between the equations (Burgers: 6 fp64 operations fewer
+    per cell; rounding differs from the unfolded form by ~1 ulp per product)."""
     builder = _LeafBuilder(spec)
-    exprs = [sp.sympify(spec.rhs[i]) for i in eq_indices]
     symbols = sorted(
         set().union(*[e.free_symbols for e in exprs]) if exprs else set(),
         key=lambda s: s.name,
     )
-    names, leaf_lines = {}, []
+    names, leaf_lines, raw_lines, subs = {}, [], [], {}
     for n, s in enumerate(symbols):
         ident = f"L{n}"
+        leaf = builder.leaf(s.name)
+        m = re.fullmatch(r"D1_(\d+)_(\d+)", leaf) if fold_first_derivatives else None
+        if m:
+            comp, axis = int(m.group(1)), int(m.group(2))
+            raw, const = f"RAW_{comp}_{axis}", f"PML_INV2H{axis}"
+            raw_lines.append(
+                f"  const double {raw} = pml_d1raw_at<{axis}>(S, {comp}, c);"
+                f"  // {s.name} * 2 h"
+            )
+            names[raw], names[const] = raw, const
+            subs[s] = sp.Symbol(const) * sp.Symbol(raw)
+            continue
         names[s.name] = ident
-        leaf_lines.append(
-            f"  const double {ident} = {builder.leaf(s.name)};  // {s.name}"
-        )
+        leaf_lines.append(f"  const double {ident} = {leaf};  // {s.name}")
+    cse_lines = []
+    if subs:
+        folded = [e.xreplace(subs) for e in exprs]
+        temps, exprs = sp.cse(folded, symbols=sp.numbered_symbols("X"))
+        for t, _ in temps:
+            names[t.name] = t.name
+        printer = _CudaPrinter(names)
+        cse_lines = [
+            f"  const double {t.name} = {printer.doprint(e)};" for t, e in temps
+        ]
     printer = _CudaPrinter(names)
     out_lines = [
         f"  out[{j}] = {printer.doprint(e)};" for j, e in enumerate(exprs)
     ]
-    prim_lines = [
-        f"  const double {p} = {builder.prims[p]};" for p in builder.order
-    ]
-    body = "\n".join(prim_lines + leaf_lines + out_lines)
+    # only the primitives something still refers to (a folded first derivative
+    # leaves its D1 primitive unused)
+    text = "\n".join(leaf_lines + cse_lines + out_lines)
+    prim_lines, needed = [], set()
+    for p_name in reversed(builder.order):
+        code = builder.prims[p_name]
+        if re.search(rf"\b{p_name}\b", text) or p_name in needed:
+            prim_lines.append(f"  const double {p_name} = {code};")
+            needed.update(re.findall(r"\b[A-Z][A-Z0-9]*(?:_\d+)*\b", code))
+    prim_lines.reverse()
+    return "\n".join(prim_lines + raw_lines + leaf_lines + cse_lines + out_lines)
+
+
+def _emit_function(fn_name: str, spec: ProblemSpec, eq_indices: Sequence[int]):
+    exprs = [sp.sympify(spec.rhs[i]) for i in eq_indices]
+    body = _emit_body(spec, exprs, False)
+    if os.environ.get("PML_FOLD_D1", "1") != "0" and spec.shape:
+        fast = _emit_body(spec, exprs, True)
+        if "pml_d1raw_at<" in fast:
+            # the all-interior instantiation has no boundary handling: its
+            # first derivatives are plain differences
+            body = (
+                "  if constexpr (IM == PML_IM_ALL) {\n" + fast
+                + "\n  } else {\n" + body + "\n  }"
+            )
     return (
         "template <int IM, class SRC>\n"
         f"__device__ __forceinline__ void {fn_name}(const PmlArgs& a, "
