@@ -76,6 +76,10 @@ def parse_args():
     p.add_argument("--parity-grid-3d", type=int, default=256)
     p.add_argument("--parity-grid-2d", type=int, default=2048)
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-stiff", action="store_true",
+                   help="N > 1: skip the Parareal solve at the harder setting")
+    p.add_argument("--stiff-coarse-ratio", type=int, default=8)
+    p.add_argument("--stiff-tol", type=float, default=1e-9)
     p.add_argument("--no-spatial", action="store_true",
                    help="N > 1: skip the slab-decomposed solve")
     p.add_argument("--spatial-steps", type=int, default=20)
@@ -1228,6 +1232,42 @@ def run_b200(args):
     launches = dv.total_launches() - launches0
     iterations = p.last_iterations
 
+    # ---- the same solve at a harder setting (coarser coarse propagator, tighter
+    # tolerance): how wall time and iteration count move when convergence is
+    # not nearly free -------------------------------------------------------
+    stiff = None
+    if not args.no_stiff:
+        try:
+            p.last_slice_trajectory = None
+            torch.cuda.empty_cache()
+            g_s = FDMOperator(
+                ForwardEulerMethod(), ThreePointCentralDifferenceMethod(),
+                d_t * args.stiff_coarse_ratio,
+            )
+            p_s = PararealOperator(f, g_s, args.stiff_tol, gather_trajectory=False)
+            p_s.solve_on_device(ivp, y0_planes)  # warm-up (coarse plan)
+            barrier()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record()
+            p_s.solve_on_device(ivp, y0_planes)
+            q1.record()
+            barrier()
+            ms_q = torch.tensor([q0.elapsed_time(q1)], dtype=torch.float64, device="cuda")
+            dist.all_reduce(ms_q, op=dist.ReduceOp.MAX)
+            stiff = {
+                "coarse_ratio": args.stiff_coarse_ratio, "tol": args.stiff_tol,
+                "wall_ms_per_solve": float(ms_q.item()),
+                "iterations": p_s.last_iterations,
+                "bound_p_over_k": world / max(p_s.last_iterations, 1),
+                "speedup_vs_serial_fine": fine_slice_ms * world / float(ms_q.item()),
+                "update_norms": [[float(v) for v in row] for row in p_s.last_update_norms],
+                "wasted_speculative_fine_steps_rank0": p_s.last_wasted_fine_steps,
+            }
+            p_s.last_slice_trajectory = None
+            del p_s
+        except Exception as exc:  # the main line must survive
+            stiff = {"error": f"{type(exc).__name__}: {str(exc)[:300]}"}
+
     e2e = None
     # the timed solves' slice trajectory (slice_steps x 3.2 GB) must not stay
     # resident next to the one the end-to-end solve allocates
@@ -1373,6 +1413,7 @@ def run_b200(args):
                 "fine_steps_per_slice": s_steps,
                 "iterations": iterations,
                 "bound_p_over_k": world / max(iterations, 1),
+                "harder_setting": stiff,
                 "note": "serial_fine_ms = the fine operator stepping all "
                         f"{total_steps} steps on one GPU (the slice solve timed "
                         "on every rank, max over ranks, x slices); the Parareal "
