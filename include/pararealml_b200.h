@@ -28,7 +28,9 @@ typedef struct pml_plan_desc {
   int n_dt, n_alg, n_lap; /* equations per LHS kind (differential_equation.py:140-149) */
   int block[3];     /* thread block shape the source was generated for */
   int fused;        /* != 0: the source has the fused stage-pair kernels
-                       (1 = barrier per plane, 2 = warp-specialised pipeline) */
+                       (1 = one thread per cell of the stage-A tile, 2 = column-
+                       marching threads with register columns; the latter also
+                       has the forward Euler step-pair kernel) */
   int fused_tile[2]; /* their tile (cells along the contiguous axis, axis 1) */
   int fused_zc;     /* planes of the marching axis per thread block */
   int fused_threads; /* threads per block of the fused kernels */
