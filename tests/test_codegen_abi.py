@@ -177,3 +177,58 @@ def test_nvrtc_compiles_the_fused_pair_kernels(tmp_path, monkeypatch):
     ).stdout
     assert "pml_fused_rk4_12" in sass and "pml_fused_rk4_34" in sass
     assert "UTMALDG" in sass and "SYNCS" in sass
+
+
+def _burgers_problem(neumann_value=0.0, static=True):
+    eq = ns.BurgersEquation(3, 100.0)
+    mesh = ns.Mesh([(0.0, 1.0)] * 3, [1.0 / 15, 1.0 / 17, 1.0 / 19])
+    bc = ns.NeumannBoundaryCondition(
+        lambda x, t: np.full((len(x), 3), neumann_value), is_static=static
+    )
+    return ns.ConstrainedProblem(eq, mesh, [(bc, bc)] * 3)
+
+
+def test_static_zero_flux_faces_are_compiled_in():
+    """Faces whose static Neumann table is 0.0 everywhere need no table
+    look-ups (PML_NEU_ZERO_MASK); any other value, or a dynamic condition,
+    keeps them."""
+    low = lower_problem(_burgers_problem(0.0))
+    assert low.neu_mask == 63 and low.neu_zero_mask == 63
+    assert "#define PML_NEU_ZERO_MASK 63" in codegen.generate_source(low.spec())
+    assert lower_problem(_burgers_problem(0.25)).neu_zero_mask == 0
+    assert lower_problem(_burgers_problem(0.0, static=False)).neu_zero_mask == 0
+    # mixed: one Dirichlet face pair, the rest zero flux
+    eq = ns.DiffusionEquation(2, 0.1)
+    mesh = ns.Mesh([(0.0, 1.0)] * 2, [0.1, 0.1])
+    dirichlet = ns.DirichletBoundaryCondition(
+        lambda x, t: np.zeros((len(x), 1)), is_static=True)
+    flux = ns.NeumannBoundaryCondition(
+        lambda x, t: np.zeros((len(x), 1)), is_static=True)
+    low = lower_problem(ns.ConstrainedProblem(eq, mesh, [(dirichlet, dirichlet), (flux, flux)]))
+    assert low.neu_mask == 0b1100 and low.neu_zero_mask == 0b1100 and low.dir_mask == 0b0011
+
+
+def test_interior_variant_folds_mesh_constants(monkeypatch):
+    """The all-interior instantiation of the generated right-hand side enters
+    first derivatives as constant x raw difference (shared products found by
+    SymPy's cse) and the Cartesian Laplacian as one FMA chain; the boundary
+    variants keep the plain primitives."""
+    low = lower_problem(_burgers_problem())
+    src = codegen.generate_source(low.spec())
+    body = src[src.index("void pml_rhs_dt("):]
+    body = body[: body.index("\n}\n")]
+    fast, general = body.split("} else {")
+    assert "if constexpr (IM == PML_IM_ALL)" in fast
+    assert fast.count("pml_d1raw_at<") == 9 and "pml_d1_at<" not in fast
+    assert re.search(r"const double X0 = PML_INV2H0\*L\d+;", fast)
+    assert general.count("pml_d1_at<") == 9 and "pml_d1raw_at<" not in general
+    assert fast.count("pml_lap_at<IM>") == 3 and general.count("pml_lap_at<IM>") == 3
+    monkeypatch.setenv("PML_FOLD_D1", "0")
+    monkeypatch.setenv("PML_FAST_LAPLACIAN", "0")
+    plain = codegen.generate_source(low.spec())
+    assert "pml_d1raw_at<0>(S" not in plain and "pml_lap_at<IM>" not in plain
+    assert plain.count("pml_d2_at<") == 9
+    # a polar mesh has metric factors in its gradients: only plain first
+    # derivatives are folded, the Laplacian keeps its coordinate-system form
+    _, polar = _source(cases.FDM_BY_NAME["shallow_water_polar_rk4"])
+    assert "pml_lap_at<IM>" not in polar
