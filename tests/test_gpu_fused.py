@@ -209,3 +209,21 @@ def test_euler_step_pairs_match_stage_kernels_and_oracle(problem, monkeypatch):
     assert per_step_rel_err(fused, staged) <= 1e-14
     _, y_oracle = oracle.fdm_solve(ivp, "forward_euler", d_t)
     assert per_step_rel_err(fused, y_oracle) <= 1e-12
+
+
+@pytest.mark.parametrize(
+    "rows,sync,variant", [("2", "0", "2"), ("1", "1", "2"), ("1", "0", "1")]
+)
+def test_pair_kernel_options_match_stage_kernels(rows, sync, variant, monkeypatch):
+    """The non-default forms of the stage-pair kernels: register tiling over
+    2 rows per thread, per-warp mbarrier arrivals instead of the block barrier,
+    and the round-1 body (one thread per cell of the stage-A tile)."""
+    monkeypatch.setenv("PML_FROWS", rows)
+    monkeypatch.setenv("PML_FSYNC", sync)
+    monkeypatch.setenv("PML_FVARIANT", variant)
+    ivp, d_t, fused, n_fused = solve("burgers_3d_default_tile", RK4, True, monkeypatch)
+    _, _, staged, n_staged = solve("burgers_3d_default_tile", RK4, False, monkeypatch)
+    assert np.isfinite(fused).all() and n_fused < n_staged
+    assert per_step_rel_err(fused, staged) <= 1e-14
+    _, y_oracle = oracle.fdm_solve(ivp, "rk4", d_t)
+    assert per_step_rel_err(fused, y_oracle) <= 1e-12
