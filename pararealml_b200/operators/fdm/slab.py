@@ -13,7 +13,11 @@ vectors are sliced to the slab.
 
 One rank per GPU with ``torch.distributed``: NCCL moves the halo planes GPU to
 GPU over NVLink; a gloo group (tests, several ranks on one GPU) stages them
-through the host.
+through the host.  With the stage-pair kernels a launch is split by planes
+(``pml_fdm_phase_planes``): the ``EDGE_PLANES`` next to each neighbour are
+computed first and their exchange -- pack, send / receive on a dedicated
+high-priority NCCL communicator, unpack, all on a high-priority side stream --
+runs while the launch of the remaining planes computes.
 """
 import ctypes
 from dataclasses import replace
